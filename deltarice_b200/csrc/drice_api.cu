@@ -1,0 +1,685 @@
+// drice_api.cu — C-ABI of include/deltarice_b200.h: parameter parsing, per-batch tables,
+// the device entry points and the chunk scheduler (host-pointer entry points).
+//
+// Host-side counterpart of the reference's chunk layer (paths relative to /root/reference):
+//   parseCD_VALUES                     src/deltaRice.c:248-291
+//   determinePowerOf2                  src/deltaRice.c:114-136
+//   writeWholeCompressedByteString     src/deltaRice.c:383-465  (per chunk -> per batch here)
+//   readWholeCompressedByteString      src/deltaRice.c:301-358
+#include "../../include/deltarice_b200.h"
+#include "drice_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace drice;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void  *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Slot {                 // one in-flight sub-batch of the chunk scheduler
+    DevBuf raw, comp, offs;   // device raw samples, device stream, device chunk byte offsets (+status)
+    cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;
+    std::vector<uint64_t> h_offs;
+    uint64_t *h_offs_pinned = nullptr;
+    size_t h_offs_cap = 0;
+    size_t c0 = 0, c1 = 0;    // chunk range
+    bool busy = false;
+};
+
+}  // namespace
+
+struct drice_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;       // default work stream
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    // per-call tables (host pinned staging + device)
+    void  *h_tab = nullptr;
+    size_t h_tab_cap = 0;
+    DevBuf d_tab;                        // chunk tables
+    DevBuf d_scratch;                    // look-back words / wave tables, ticket, status
+    cudaEvent_t ev_tab = nullptr;        // tables uploaded (h_tab reusable)
+    bool ev_tab_pending = false;
+
+    // synchronous-call helpers
+    DevBuf d_offs;                       // chunk byte offsets + status for the *_dev sync forms
+    uint64_t *h_sync = nullptr;          // pinned landing zone
+    size_t h_sync_cap = 0;
+
+    Slot slots[3];
+};
+
+namespace {
+
+int fail(drice_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+int cuda_fail(drice_ctx *ctx, cudaError_t e, const char *what)
+{
+    return fail(ctx, DRICE_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define DR_CUDA(ctx, call)                                         \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+size_t wave_bound_words(size_t n) { return (25 * n + 31) / 32; }
+
+// geometry of a batch derived from the caller's chunk sizes
+struct Geometry {
+    std::vector<uint32_t> wave_off;    // [nchunks+1]
+    uint32_t nwaves = 0;
+    uint32_t uniform_wpc = 0;
+    uint32_t max_wave = 0;
+    uint32_t Lk = 0;                   // kernel L (0 = whole chunk)
+    bool     wave_offsets_mult4 = true;
+};
+
+int build_geometry(drice_ctx *ctx, const uint64_t *off, size_t nchunks, int64_t L, bool encode, Geometry &g)
+{
+    if (L == 0 || L < -1) return fail(ctx, DRICE_E_PARAM, "WaveformLength must be -1 or >= 1");
+    if (L > 0x7fffffffll) return fail(ctx, DRICE_E_PARAM, "WaveformLength too large");
+    if (nchunks > 0x7ffffffeull) return fail(ctx, DRICE_E_PARAM, "too many chunks");
+    g.Lk = L < 0 ? 0u : (uint32_t)L;
+    g.wave_off.resize(nchunks + 1);
+    uint64_t nw = 0;
+    bool uniform = true;
+    uint64_t first_w = 0;
+    for (size_t c = 0; c < nchunks; ++c) {
+        if (off[c + 1] < off[c]) return fail(ctx, DRICE_E_PARAM, "chunk_sample_off must be non-decreasing");
+        const uint64_t total = off[c + 1] - off[c];
+        // per-chunk counts are 32-bit ints in the format (src/deltaRice.c:306,:389)
+        if (total > 0x7fffffffull) return fail(ctx, DRICE_E_PARAM, "chunk larger than 2^31-1 samples");
+        const uint64_t Lw = g.Lk ? g.Lk : total;
+        uint64_t w = total ? (total + Lw - 1) / Lw : 0;
+        if (encode && total == 0) w = 1;      // pseudo wave: emits the [0] chunk header
+        g.wave_off[c] = (uint32_t)nw;
+        if (c == 0) first_w = w; else if (w != first_w) uniform = false;
+        nw += w;
+        if (nw > 0xfffffff0ull) return fail(ctx, DRICE_E_PARAM, "too many waves in one batch");
+        g.max_wave = std::max<uint32_t>(g.max_wave, (uint32_t)std::min<uint64_t>(Lw, total));
+        if ((off[c] & 3) || (w > 1 && (Lw & 3))) g.wave_offsets_mult4 = false;
+    }
+    g.wave_off[nchunks] = (uint32_t)nw;
+    g.nwaves = (uint32_t)nw;
+    g.uniform_wpc = (uniform && nchunks > 0 && first_w > 0) ? (uint32_t)first_w : 0u;
+    return DRICE_OK;
+}
+
+// uploads [chunk_sample_off u64 (n+1)] [second u64 table (n+1), optional] [wave_off u32 (n+1)]
+int upload_tables(drice_ctx *ctx, const uint64_t *t0, const uint64_t *t1, const uint32_t *wave_off,
+                  size_t nchunks, cudaStream_t st, uint64_t **d_t0, uint64_t **d_t1, uint32_t **d_w)
+{
+    const size_t n1 = nchunks + 1;
+    const size_t bytes = n1 * 8 * 2 + n1 * 4;
+    if (ctx->ev_tab_pending) {
+        DR_CUDA(ctx, cudaEventSynchronize(ctx->ev_tab));
+        ctx->ev_tab_pending = false;
+    }
+    if (bytes > ctx->h_tab_cap) {
+        if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
+        ctx->h_tab = nullptr;
+        ctx->h_tab_cap = 0;
+        DR_CUDA(ctx, cudaMallocHost(&ctx->h_tab, bytes * 2));
+        ctx->h_tab_cap = bytes * 2;
+    }
+    // the previous call's kernels may still read d_tab: same-stream ordering covers `st`;
+    // growing the buffer frees it, so drain first
+    if (bytes > ctx->d_tab.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
+    DR_CUDA(ctx, ctx->d_tab.reserve(bytes));
+    char *h = (char *)ctx->h_tab;
+    memcpy(h, t0, n1 * 8);
+    if (t1) memcpy(h + n1 * 8, t1, n1 * 8); else memset(h + n1 * 8, 0, n1 * 8);
+    memcpy(h + n1 * 16, wave_off, n1 * 4);
+    DR_CUDA(ctx, cudaMemcpyAsync(ctx->d_tab.p, h, bytes, cudaMemcpyHostToDevice, st));
+    DR_CUDA(ctx, cudaEventRecord(ctx->ev_tab, st));
+    ctx->ev_tab_pending = true;
+    *d_t0 = (uint64_t *)ctx->d_tab.p;
+    *d_t1 = (uint64_t *)((char *)ctx->d_tab.p + n1 * 8);
+    *d_w = (uint32_t *)((char *)ctx->d_tab.p + n1 * 16);
+    return DRICE_OK;
+}
+
+int status_to_error(drice_ctx *ctx, uint32_t status)
+{
+    if (status == 0) return DRICE_OK;
+    if (status & kErrCapacity) return fail(ctx, DRICE_E_CAPACITY, "output buffer too small for the compressed batch");
+    if (status & kErrTotal) return fail(ctx, DRICE_E_STREAM, "chunk stream's sample count differs from the expected chunk size");
+    return fail(ctx, DRICE_E_STREAM, "malformed Delta-Rice stream");
+}
+
+}  // namespace
+
+// ======================================================================================
+// parameter helpers
+// ======================================================================================
+extern "C" int drice_abi_version(void) { return DRICE_ABI_VERSION; }
+
+extern "C" int drice_log2_param(int M)
+{
+    if (M <= 0 || (M & (M - 1)) != 0) return -1;
+    int k = 0;
+    while ((1 << k) != M) ++k;
+    return k <= 15 ? k : -1;    // M >= 65536 corrupts the reference stream
+}
+
+extern "C" int drice_parse_cd_values(size_t n, const unsigned int *cd, drice_params *out)
+{
+    if (!out || (n > 0 && !cd)) return DRICE_E_PARAM;
+    memset(out, 0, sizeof(*out));
+    out->M = 8;                 // defaults, src/deltaRice.c:249-257
+    out->L = -1;
+    out->filter_len = 2;
+    out->filter[0] = 1;
+    out->filter[1] = -1;
+    if (n >= 1) out->M = (int32_t)cd[0];
+    if (n >= 2) out->L = (int32_t)cd[1];
+    if (n >= 3) {
+        out->filter_len = (int32_t)cd[2];
+        if (out->filter_len <= 0 || (size_t)out->filter_len + 3 > n) return DRICE_E_PARAM;
+        if (out->filter_len > 8) return DRICE_E_UNSUPPORTED;
+        for (int f = 0; f < out->filter_len; ++f) out->filter[f] = (int32_t)cd[3 + f];
+        // only the delta filter [1,-1] is on the GPU path; anything else is refused rather
+        // than mis-encoded (no CPU fallback)
+        if (!(out->filter_len == 2 && out->filter[0] == 1 && out->filter[1] == -1)) return DRICE_E_UNSUPPORTED;
+    }
+    if (drice_log2_param(out->M) < 0) return DRICE_E_PARAM;
+    if (out->L == 0 || out->L < -1) return DRICE_E_PARAM;
+    return DRICE_OK;
+}
+
+extern "C" size_t drice_chunk_bound_bytes(size_t total, int64_t L)
+{
+    if (total == 0) return 4;
+    size_t Lw = (L <= 0 || (uint64_t)L > total) ? total : (size_t)L;
+    size_t W = (total + Lw - 1) / Lw;
+    size_t tail = total - (W - 1) * Lw;
+    return 4 * (1 + W + (W - 1) * wave_bound_words(Lw) + wave_bound_words(tail));
+}
+
+extern "C" size_t drice_batch_bound_bytes(const uint64_t *off, size_t nchunks, int64_t L)
+{
+    size_t b = 0;
+    for (size_t c = 0; c < nchunks; ++c) b += drice_chunk_bound_bytes((size_t)(off[c + 1] - off[c]), L);
+    return b;
+}
+
+// ======================================================================================
+// context
+// ======================================================================================
+extern "C" int drice_create(drice_ctx **out, int device)
+{
+    if (!out) return DRICE_E_PARAM;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, DRICE_E_CUDA, std::string("no usable CUDA device (this library has no CPU path): ") +
+                                               cudaGetErrorString(e));
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= ndev) return fail(nullptr, DRICE_E_PARAM, "device index out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major < 10)
+        return fail(nullptr, DRICE_E_CUDA, std::string("device ") + prop.name + " is not sm_100-class; kernels are built for sm_100a only");
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    drice_ctx *ctx = new (std::nothrow) drice_ctx();
+    if (!ctx) return fail(nullptr, DRICE_E_NOMEM, "out of memory");
+    ctx->device = device;
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_tab, cudaEventDisableTiming) == cudaSuccess;
+    for (Slot &s : ctx->slots)
+        ok = ok && cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        std::string m = std::string("stream/event creation failed: ") + cudaGetErrorString(cudaGetLastError());
+        drice_destroy(ctx);
+        return fail(nullptr, DRICE_E_CUDA, m);
+    }
+    *out = ctx;
+    return DRICE_OK;
+}
+
+extern "C" void drice_destroy(drice_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (Slot &s : ctx->slots) {
+        s.raw.release(); s.comp.release(); s.offs.release();
+        if (s.ev_in) cudaEventDestroy(s.ev_in);
+        if (s.ev_k) cudaEventDestroy(s.ev_k);
+        if (s.ev_out) cudaEventDestroy(s.ev_out);
+        if (s.h_offs_pinned) cudaFreeHost(s.h_offs_pinned);
+    }
+    ctx->d_tab.release(); ctx->d_scratch.release(); ctx->d_offs.release();
+    if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
+    if (ctx->h_sync) cudaFreeHost(ctx->h_sync);
+    if (ctx->ev_tab) cudaEventDestroy(ctx->ev_tab);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    delete ctx;
+}
+
+extern "C" const char *drice_last_error(const drice_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+extern "C" int drice_device(const drice_ctx *ctx) { return ctx ? ctx->device : -1; }
+extern "C" uint64_t drice_launch_count(const drice_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" void *drice_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void drice_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ======================================================================================
+// device entry points
+// ======================================================================================
+extern "C" int drice_encode_batch_dev_async(drice_ctx *ctx, const int16_t *d_raw, const uint64_t *off,
+                                            size_t nchunks, int M, int64_t L, uint32_t *d_out,
+                                            size_t out_cap_bytes, uint64_t *d_chunk_byte_off,
+                                            uint32_t *d_status, void *stream)
+{
+    if (!ctx) return DRICE_E_PARAM;
+    if (!off || !d_chunk_byte_off || !d_status) return fail(ctx, DRICE_E_PARAM, "null argument");
+    const int k = drice_log2_param(M);
+    if (k < 0) return fail(ctx, DRICE_E_PARAM, "RiceParameter must be a power of two in [1, 32768]");
+    if ((reinterpret_cast<uintptr_t>(d_out) & 3) || (reinterpret_cast<uintptr_t>(d_raw) & 1))
+        return fail(ctx, DRICE_E_PARAM, "misaligned buffer");
+    DR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    Geometry g;
+    int rc = build_geometry(ctx, off, nchunks, L, true, g);
+    if (rc) return rc;
+    DR_CUDA(ctx, cudaMemsetAsync(d_status, 0, sizeof(uint32_t), st));
+    if (nchunks == 0) {
+        DR_CUDA(ctx, cudaMemsetAsync(d_chunk_byte_off, 0, sizeof(uint64_t), st));
+        return DRICE_OK;
+    }
+    if (!d_raw && off[nchunks] > 0) return fail(ctx, DRICE_E_PARAM, "null input");
+    uint64_t *d_soff, *d_unused;
+    uint32_t *d_woff;
+    rc = upload_tables(ctx, off, nullptr, g.wave_off.data(), nchunks, st, &d_soff, &d_unused, &d_woff);
+    if (rc) return rc;
+    const size_t scratch = (size_t)g.nwaves * 8 + 16;
+    if (scratch > ctx->d_scratch.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
+    DR_CUDA(ctx, ctx->d_scratch.reserve(scratch));
+    DR_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch.p, 0, scratch, st));
+
+    EncodeParams p{};
+    p.raw = d_raw;
+    p.raw_samples = off[nchunks];
+    p.out = d_out;
+    p.out_cap_words = out_cap_bytes / 4;
+    p.chunk_sample_off = d_soff;
+    p.chunk_wave_off = d_woff;
+    p.chunk_byte_off = d_chunk_byte_off;
+    p.ticket = (uint32_t *)ctx->d_scratch.p;
+    p.lookback = (uint64_t *)((char *)ctx->d_scratch.p + 16);
+    p.status = d_status;
+    p.nchunks = (uint32_t)nchunks;
+    p.nwaves = g.nwaves;
+    p.uniform_wpc = g.uniform_wpc;
+    p.L = g.Lk;
+    p.k = k;
+    int nl = launch_encode(p, g.max_wave, st);
+    if (nl < 0) return fail(ctx, DRICE_E_PARAM, "unsupported RiceParameter");
+    ctx->launches += (uint64_t)nl;
+    DR_CUDA(ctx, cudaGetLastError());
+    return DRICE_OK;
+}
+
+namespace {
+int ensure_sync_buffers(drice_ctx *ctx, size_t nchunks)
+{
+    const size_t bytes = (nchunks + 1) * 8 + 8;
+    DR_CUDA(ctx, ctx->d_offs.reserve(bytes));
+    if (bytes > ctx->h_sync_cap) {
+        if (ctx->h_sync) cudaFreeHost(ctx->h_sync);
+        ctx->h_sync = nullptr;
+        ctx->h_sync_cap = 0;
+        DR_CUDA(ctx, cudaMallocHost((void **)&ctx->h_sync, bytes * 2));
+        ctx->h_sync_cap = bytes * 2;
+    }
+    return DRICE_OK;
+}
+}  // namespace
+
+extern "C" int drice_encode_batch_dev(drice_ctx *ctx, const int16_t *d_raw, const uint64_t *off,
+                                      size_t nchunks, int M, int64_t L, uint32_t *d_out,
+                                      size_t out_cap_bytes, uint64_t *chunk_byte_off, void *stream)
+{
+    if (!ctx) return DRICE_E_PARAM;
+    if (!chunk_byte_off) return fail(ctx, DRICE_E_PARAM, "null argument");
+    DR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    int rc = ensure_sync_buffers(ctx, nchunks);
+    if (rc) return rc;
+    uint64_t *d_offs = (uint64_t *)ctx->d_offs.p;
+    uint32_t *d_status = (uint32_t *)(d_offs + nchunks + 1);
+    rc = drice_encode_batch_dev_async(ctx, d_raw, off, nchunks, M, L, d_out, out_cap_bytes, d_offs, d_status, st);
+    if (rc) return rc;
+    const size_t bytes = (nchunks + 1) * 8 + 8;
+    DR_CUDA(ctx, cudaMemcpyAsync(ctx->h_sync, d_offs, bytes, cudaMemcpyDeviceToHost, st));
+    DR_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint32_t status = *(uint32_t *)(ctx->h_sync + nchunks + 1);
+    memcpy(chunk_byte_off, ctx->h_sync, (nchunks + 1) * 8);
+    return status_to_error(ctx, status);
+}
+
+extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_comp, const uint64_t *boff,
+                                            size_t nchunks, const uint64_t *off, int M, int64_t L,
+                                            int16_t *d_out, uint32_t *d_status, void *stream)
+{
+    if (!ctx) return DRICE_E_PARAM;
+    if (!boff || !off || !d_status) return fail(ctx, DRICE_E_PARAM, "null argument");
+    const int k = drice_log2_param(M);
+    if (k < 0) return fail(ctx, DRICE_E_PARAM, "RiceParameter must be a power of two in [1, 32768]");
+    if ((reinterpret_cast<uintptr_t>(d_comp) & 3) || (reinterpret_cast<uintptr_t>(d_out) & 1))
+        return fail(ctx, DRICE_E_PARAM, "misaligned buffer");
+    DR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    Geometry g;
+    int rc = build_geometry(ctx, off, nchunks, L, false, g);
+    if (rc) return rc;
+    DR_CUDA(ctx, cudaMemsetAsync(d_status, 0, sizeof(uint32_t), st));
+    if (nchunks == 0) return DRICE_OK;
+    std::vector<uint64_t> woff(nchunks + 1);
+    for (size_t c = 0; c <= nchunks; ++c) {
+        if ((boff[c] & 3) || (c && boff[c] < boff[c - 1] + 4))
+            return fail(ctx, DRICE_E_PARAM, "chunk_byte_off must be 4-byte multiples, each chunk >= 4 bytes");
+        woff[c] = boff[c] / 4;
+    }
+    if (!d_comp) return fail(ctx, DRICE_E_PARAM, "null input");
+    uint64_t *d_soff, *d_woff64;
+    uint32_t *d_wave_off;
+    rc = upload_tables(ctx, off, woff.data(), g.wave_off.data(), nchunks, st, &d_soff, &d_woff64, &d_wave_off);
+    if (rc) return rc;
+    const size_t nw = g.nwaves;
+    const size_t scratch = nw * (8 + 8 + 4) + 64;
+    if (scratch > ctx->d_scratch.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
+    DR_CUDA(ctx, ctx->d_scratch.reserve(scratch));
+    uint64_t *wave_in = (uint64_t *)ctx->d_scratch.p;
+    uint64_t *wave_out = wave_in + nw;
+    uint32_t *wave_n = (uint32_t *)(wave_out + nw);
+
+    LocateParams lp{};
+    lp.comp = d_comp;
+    lp.comp_words = woff[nchunks];
+    lp.chunk_word_off = d_woff64;
+    lp.chunk_sample_off = d_soff;
+    lp.chunk_wave_off = d_wave_off;
+    lp.wave_in = wave_in;
+    lp.wave_out = wave_out;
+    lp.wave_n = wave_n;
+    lp.status = d_status;
+    lp.nchunks = (uint32_t)nchunks;
+    lp.L = g.Lk;
+    ctx->launches += (uint64_t)launch_locate(lp, st);
+
+    ParseParams pp{};
+    pp.comp = d_comp;
+    pp.comp_words = woff[nchunks];
+    pp.wave_in = wave_in;
+    pp.wave_out = wave_out;
+    pp.wave_n = wave_n;
+    pp.out = d_out;
+    pp.status = d_status;
+    pp.nwaves = g.nwaves;
+    pp.max_n = g.max_wave;
+    pp.k = k;
+    const bool wide = g.wave_offsets_mult4 && (reinterpret_cast<uintptr_t>(d_out) & 7) == 0;
+    int nl = launch_parse(pp, wide ? 8 : 2, st);
+    if (nl < 0) return fail(ctx, DRICE_E_PARAM, "unsupported RiceParameter");
+    ctx->launches += (uint64_t)nl;
+    DR_CUDA(ctx, cudaGetLastError());
+    return DRICE_OK;
+}
+
+extern "C" int drice_decode_batch_dev(drice_ctx *ctx, const uint32_t *d_comp, const uint64_t *boff,
+                                      size_t nchunks, const uint64_t *off, int M, int64_t L,
+                                      int16_t *d_out, void *stream)
+{
+    if (!ctx) return DRICE_E_PARAM;
+    DR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    int rc = ensure_sync_buffers(ctx, 0);
+    if (rc) return rc;
+    uint32_t *d_status = (uint32_t *)ctx->d_offs.p;
+    rc = drice_decode_batch_dev_async(ctx, d_comp, boff, nchunks, off, M, L, d_out, d_status, st);
+    if (rc) return rc;
+    DR_CUDA(ctx, cudaMemcpyAsync(ctx->h_sync, d_status, 4, cudaMemcpyDeviceToHost, st));
+    DR_CUDA(ctx, cudaStreamSynchronize(st));
+    return status_to_error(ctx, *(uint32_t *)ctx->h_sync);
+}
+
+// ======================================================================================
+// chunk scheduler: host-pointer entry points
+// ======================================================================================
+namespace {
+
+size_t subbatch_bytes()
+{
+    static size_t v = 0;
+    if (!v) {
+        const char *e = getenv("DRICE_SUBBATCH_MB");
+        long mb = e ? atol(e) : 64;
+        if (mb < 1) mb = 1;
+        v = (size_t)mb << 20;
+    }
+    return v;
+}
+
+int slot_offs_reserve(drice_ctx *ctx, Slot &s, size_t nchunks)
+{
+    const size_t bytes = (nchunks + 1) * 8 + 8;
+    DR_CUDA(ctx, s.offs.reserve(bytes));
+    if (bytes > s.h_offs_cap) {
+        if (s.h_offs_pinned) cudaFreeHost(s.h_offs_pinned);
+        s.h_offs_pinned = nullptr;
+        s.h_offs_cap = 0;
+        DR_CUDA(ctx, cudaMallocHost((void **)&s.h_offs_pinned, bytes * 2));
+        s.h_offs_cap = bytes * 2;
+    }
+    return DRICE_OK;
+}
+
+// cuts [0,nchunks) into runs of whole chunks of about `target` raw bytes
+std::vector<size_t> cut_subbatches(const uint64_t *off, size_t nchunks, size_t target)
+{
+    std::vector<size_t> cuts{0};
+    size_t c = 0;
+    while (c < nchunks) {
+        size_t e = c + 1;
+        while (e < nchunks && (off[e + 1] - off[c]) * 2 <= target) ++e;
+        cuts.push_back(e);
+        c = e;
+    }
+    return cuts;
+}
+
+}  // namespace
+
+extern "C" int drice_encode_batch_host(drice_ctx *ctx, const int16_t *h_raw, const uint64_t *off,
+                                       size_t nchunks, int M, int64_t L, void *h_out,
+                                       size_t out_cap_bytes, uint64_t *chunk_byte_off)
+{
+    if (!ctx) return DRICE_E_PARAM;
+    if (!off || !chunk_byte_off || (!h_out && out_cap_bytes)) return fail(ctx, DRICE_E_PARAM, "null argument");
+    if (drice_log2_param(M) < 0) return fail(ctx, DRICE_E_PARAM, "RiceParameter must be a power of two in [1, 32768]");
+    DR_CUDA(ctx, cudaSetDevice(ctx->device));
+    chunk_byte_off[0] = 0;
+    if (nchunks == 0) return DRICE_OK;
+    const std::vector<size_t> cuts = cut_subbatches(off, nchunks, subbatch_bytes());
+    const size_t nsub = cuts.size() - 1;
+    constexpr int NS = 3;
+    uint64_t out_pos = 0;      // bytes written to h_out so far (known once a sub-batch's kernel is done)
+    int rc = DRICE_OK;
+
+    // software pipeline: stage i = [H2D + kernels + offsets D2H] ; stage i-1 = [wait kernels,
+    // issue stream D2H at its final position]
+    auto finish = [&](size_t i) -> int {
+        Slot &s = ctx->slots[i % NS];
+        DR_CUDA(ctx, cudaEventSynchronize(s.ev_k));
+        const size_t n = s.c1 - s.c0;
+        const uint32_t status = *(uint32_t *)(s.h_offs_pinned + n + 1);
+        int r = status_to_error(ctx, status);
+        if (r) return r;
+        const uint64_t bytes = s.h_offs_pinned[n];
+        if (out_pos + bytes > out_cap_bytes) return fail(ctx, DRICE_E_CAPACITY, "output buffer too small for the compressed batch");
+        for (size_t c = 0; c <= n; ++c) chunk_byte_off[s.c0 + c] = out_pos + s.h_offs_pinned[c];
+        DR_CUDA(ctx, cudaMemcpyAsync((char *)h_out + out_pos, s.comp.p, bytes, cudaMemcpyDeviceToHost, ctx->s_out));
+        DR_CUDA(ctx, cudaEventRecord(s.ev_out, ctx->s_out));
+        out_pos += bytes;
+        return DRICE_OK;
+    };
+
+    for (size_t i = 0; i < nsub + 1 && rc == DRICE_OK; ++i) {
+        if (i < nsub) {
+            Slot &s = ctx->slots[i % NS];
+            if (s.busy) {                                  // slot's previous D2H must have drained
+                DR_CUDA(ctx, cudaEventSynchronize(s.ev_out));
+                s.busy = false;
+            }
+            s.c0 = cuts[i];
+            s.c1 = cuts[i + 1];
+            const size_t n = s.c1 - s.c0;
+            const uint64_t s0 = off[s.c0], s1 = off[s.c1];
+            s.h_offs.assign(off + s.c0, off + s.c1 + 1);
+            for (uint64_t &v : s.h_offs) v -= s0;
+            const size_t bound = drice_batch_bound_bytes(s.h_offs.data(), n, L);
+            if (s.raw.cap < (s1 - s0) * 2 + 64 || s.comp.cap < bound) DR_CUDA(ctx, cudaDeviceSynchronize());
+            DR_CUDA(ctx, s.raw.reserve((s1 - s0) * 2 + 64));
+            DR_CUDA(ctx, s.comp.reserve(bound));
+            if ((rc = slot_offs_reserve(ctx, s, n))) break;
+            DR_CUDA(ctx, cudaMemcpyAsync(s.raw.p, h_raw + s0, (s1 - s0) * 2, cudaMemcpyHostToDevice, ctx->s_in));
+            DR_CUDA(ctx, cudaEventRecord(s.ev_in, ctx->s_in));
+            DR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_in, 0));
+            uint64_t *d_offs = (uint64_t *)s.offs.p;
+            uint32_t *d_status = (uint32_t *)(d_offs + n + 1);
+            rc = drice_encode_batch_dev_async(ctx, (const int16_t *)s.raw.p, s.h_offs.data(), n, M, L,
+                                              (uint32_t *)s.comp.p, s.comp.cap, d_offs, d_status, ctx->stream);
+            if (rc) break;
+            DR_CUDA(ctx, cudaMemcpyAsync(s.h_offs_pinned, d_offs, (n + 1) * 8 + 8, cudaMemcpyDeviceToHost, ctx->stream));
+            DR_CUDA(ctx, cudaEventRecord(s.ev_k, ctx->stream));
+            s.busy = true;
+        }
+        if (i >= 1) rc = finish(i - 1);
+    }
+    // drain
+    cudaError_t e = cudaStreamSynchronize(ctx->s_out);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->s_in);
+    for (Slot &s : ctx->slots) s.busy = false;
+    if (rc == DRICE_OK && e != cudaSuccess) return cuda_fail(ctx, e, "cudaStreamSynchronize");
+    return rc;
+}
+
+extern "C" int drice_decode_batch_host(drice_ctx *ctx, const void *h_comp, const uint64_t *boff,
+                                       size_t nchunks, const uint64_t *off, int M, int64_t L,
+                                       int16_t *h_out)
+{
+    if (!ctx) return DRICE_E_PARAM;
+    if (!boff || !off) return fail(ctx, DRICE_E_PARAM, "null argument");
+    if (drice_log2_param(M) < 0) return fail(ctx, DRICE_E_PARAM, "RiceParameter must be a power of two in [1, 32768]");
+    DR_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (nchunks == 0) return DRICE_OK;
+    const std::vector<size_t> cuts = cut_subbatches(off, nchunks, subbatch_bytes());
+    const size_t nsub = cuts.size() - 1;
+    constexpr int NS = 3;
+    int rc = DRICE_OK;
+    for (size_t i = 0; i < nsub && rc == DRICE_OK; ++i) {
+        Slot &s = ctx->slots[i % NS];
+        if (s.busy) {
+            DR_CUDA(ctx, cudaEventSynchronize(s.ev_out));
+            s.busy = false;
+            const uint32_t status = *(uint32_t *)s.h_offs_pinned;
+            if ((rc = status_to_error(ctx, status))) break;
+        }
+        s.c0 = cuts[i];
+        s.c1 = cuts[i + 1];
+        const size_t n = s.c1 - s.c0;
+        const uint64_t s0 = off[s.c0], s1 = off[s.c1];
+        const uint64_t b0 = boff[s.c0], b1 = boff[s.c1];
+        if (b1 < b0 || (b0 & 3) || (b1 & 3)) { rc = fail(ctx, DRICE_E_PARAM, "chunk_byte_off must be non-decreasing 4-byte multiples"); break; }
+        s.h_offs.resize(2 * (n + 1));
+        for (size_t c = 0; c <= n; ++c) {
+            s.h_offs[c] = off[s.c0 + c] - s0;
+            s.h_offs[n + 1 + c] = boff[s.c0 + c] - b0;
+        }
+        if (s.raw.cap < (s1 - s0) * 2 + 64 || s.comp.cap < (b1 - b0) + 64) DR_CUDA(ctx, cudaDeviceSynchronize());
+        DR_CUDA(ctx, s.raw.reserve((s1 - s0) * 2 + 64));
+        DR_CUDA(ctx, s.comp.reserve((b1 - b0) + 64));
+        if ((rc = slot_offs_reserve(ctx, s, 1))) break;
+        DR_CUDA(ctx, cudaMemcpyAsync(s.comp.p, (const char *)h_comp + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->s_in));
+        DR_CUDA(ctx, cudaEventRecord(s.ev_in, ctx->s_in));
+        DR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_in, 0));
+        uint32_t *d_status = (uint32_t *)s.offs.p;
+        rc = drice_decode_batch_dev_async(ctx, (const uint32_t *)s.comp.p, s.h_offs.data() + n + 1, n,
+                                          s.h_offs.data(), M, L, (int16_t *)s.raw.p, d_status, ctx->stream);
+        if (rc) break;
+        DR_CUDA(ctx, cudaEventRecord(s.ev_k, ctx->stream));
+        DR_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, s.ev_k, 0));
+        DR_CUDA(ctx, cudaMemcpyAsync(s.h_offs_pinned, d_status, 4, cudaMemcpyDeviceToHost, ctx->s_out));
+        DR_CUDA(ctx, cudaMemcpyAsync(h_out + s0, s.raw.p, (s1 - s0) * 2, cudaMemcpyDeviceToHost, ctx->s_out));
+        DR_CUDA(ctx, cudaEventRecord(s.ev_out, ctx->s_out));
+        s.busy = true;
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->s_out);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->s_in);
+    for (Slot &s : ctx->slots) {
+        if (s.busy && rc == DRICE_OK && e == cudaSuccess) rc = status_to_error(ctx, *(uint32_t *)s.h_offs_pinned);
+        s.busy = false;
+    }
+    if (rc == DRICE_OK && e != cudaSuccess) return cuda_fail(ctx, e, "cudaStreamSynchronize");
+    return rc;
+}
+
+extern "C" int drice_peek_chunk_samples(const void *h_comp, const uint64_t *boff, size_t nchunks,
+                                        uint64_t *chunk_samples)
+{
+    if (!h_comp || !boff || !chunk_samples) return DRICE_E_PARAM;
+    for (size_t c = 0; c < nchunks; ++c) {
+        if (boff[c + 1] < boff[c] + 4) return DRICE_E_STREAM;
+        uint32_t t;
+        memcpy(&t, (const char *)h_comp + boff[c], 4);
+        chunk_samples[c] = t;
+    }
+    return DRICE_OK;
+}

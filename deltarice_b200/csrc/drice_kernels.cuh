@@ -1,0 +1,77 @@
+// drice_kernels.cuh — kernel parameter blocks and launcher prototypes (internal).
+//
+// Data layout in HBM:
+//   raw      int16 samples, all chunks of a batch back to back
+//   comp     uint32 words, chunk streams back to back:
+//            chunk := [total][record...], record := [nwords][words...]
+//   per-batch tables (device): chunk_sample_off[n+1] u64, chunk_wave_off[n+1] u32,
+//            chunk_word_off[n+1] u64; per-wave tables for decode: wave_in (u64 word index of
+//            the record header), wave_out (u64 sample offset), wave_n (u32 samples)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace drice {
+
+constexpr int      kSamplesPerThread = 16;   // one 32-byte aligned slot per thread
+constexpr uint32_t kEscapeQuotient   = 8;    // reference "giveup", src/deltaRice.c:203
+constexpr uint32_t kEscapeBits       = 25;   // 8 zeros + 1 + 16 value bits
+constexpr int      kEncMaxThreads    = 512;  // single-tile encoder: L <= 512*16-15
+constexpr int      kEncTileMaxL      = kEncMaxThreads * kSamplesPerThread - (kSamplesPerThread - 1);
+
+// status flags
+constexpr uint32_t kErrCapacity = 1u;   // output capacity exceeded
+constexpr uint32_t kErrStream   = 2u;   // malformed stream (bad counts / unary run > 8)
+constexpr uint32_t kErrTotal    = 4u;   // chunk's own sample count != expected
+
+struct EncodeParams {
+    const int16_t  *raw;
+    uint64_t        raw_samples;        // total samples in `raw` (vector-load guard)
+    uint32_t       *out;
+    uint64_t        out_cap_words;
+    const uint64_t *chunk_sample_off;   // [nchunks+1]
+    const uint32_t *chunk_wave_off;     // [nchunks+1]
+    uint64_t       *chunk_byte_off;     // [nchunks+1] result (BYTE offsets of the chunk streams)
+    uint64_t       *lookback;           // [nwaves], zeroed
+    uint32_t       *ticket;             // zeroed
+    uint32_t       *status;             // error flags (OR-ed)
+    uint32_t        nchunks;
+    uint32_t        nwaves;
+    uint32_t        uniform_wpc;        // >0: every chunk has exactly this many waves
+    uint32_t        L;                  // 0 = whole chunk is one wave
+    int             k;
+};
+
+struct LocateParams {
+    const uint32_t *comp;
+    uint64_t        comp_words;         // total words in comp (load guard)
+    const uint64_t *chunk_word_off;     // [nchunks+1] (words)
+    const uint64_t *chunk_sample_off;   // [nchunks+1]
+    const uint32_t *chunk_wave_off;     // [nchunks+1]
+    uint64_t       *wave_in;            // [nwaves]
+    uint64_t       *wave_out;           // [nwaves]
+    uint32_t       *wave_n;             // [nwaves]
+    uint32_t       *status;
+    uint32_t        nchunks;
+    uint32_t        L;                  // 0 = whole chunk
+};
+
+struct ParseParams {
+    const uint32_t *comp;
+    uint64_t        comp_words;
+    const uint64_t *wave_in;
+    const uint64_t *wave_out;
+    const uint32_t *wave_n;
+    int16_t        *out;
+    uint32_t       *status;
+    uint32_t        nwaves;
+    uint32_t        max_n;              // longest wave in the batch
+    int             k;
+};
+
+// launchers (drice_encode.cu / drice_decode.cu); return launches enqueued
+int launch_encode(const EncodeParams &p, uint32_t max_wave_len, cudaStream_t st);
+int launch_locate(const LocateParams &p, cudaStream_t st);
+int launch_parse(const ParseParams &p, int store_bytes, cudaStream_t st);
+
+}  // namespace drice

@@ -1,0 +1,146 @@
+// h5z_deltarice.cpp — the HDF5 boundary: filter class 32025, the filter callback, the
+// registration helper and the dynamic-plugin entry points.
+//
+// Replaces (reference, paths relative to /root/reference):
+//   H5Z_DELTARICE class struct         src/deltaRice.c:19-28
+//   H5Z_filter_deltarice               src/deltaRice.c:468-490
+//   deltarice_register_h5filter        src/deltaRice.c:494-501
+//   H5PLget_plugin_type / _info        src/deltaRice_h5plugin.c:4-5
+//
+// libhdf5 calls the filter once per chunk, synchronously: a batch of one chunk goes through
+// the chunk scheduler (drice_*_batch_host).  There is no CPU codec behind this file: when no
+// B200-class device is usable the callback fails (returns 0) and says why on stderr.
+//
+// Deliberate differences from the reference:
+//   B1  H5PLget_plugin_info returns the class pointer (reference returns (void*)32025)
+//   B2  failure returns 0 (reference returns (size_t)-1) and leaves *buf untouched
+//   B5/B9/B10  invalid M, WaveformLength 0, odd byte counts, empty filters are rejected
+//   generic pre-filters (cd_nelmts >= 3 other than [1,-1]) are refused, not mis-encoded
+#include "../../include/deltaRice.h"
+#include "../../include/deltarice_b200.h"
+#ifdef DRICE_USE_SYSTEM_HDF5
+#include "H5PLextern.h"
+#else
+#include "../../include/hdf5_abi/H5PLextern.h"
+#endif
+
+#include <dlfcn.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+namespace {
+std::mutex g_mu;
+drice_ctx *g_ctx = nullptr;
+
+drice_ctx *global_ctx()
+{
+    if (!g_ctx) {
+        int dev = -1;
+        if (const char *e = getenv("DRICE_DEVICE")) dev = atoi(e);
+        if (drice_create(&g_ctx, dev) != DRICE_OK) {
+            fprintf(stderr, "deltarice_b200: %s\n", drice_last_error(nullptr));
+            g_ctx = nullptr;
+        }
+    }
+    return g_ctx;
+}
+}  // namespace
+
+extern "C" {
+
+H5Z_class_t H5Z_DELTARICE[1] = {{
+    H5Z_CLASS_T_VERS,                       /* H5Z_class_t version        */
+    (H5Z_filter_t)H5Z_FILTER_DELTARICE,     /* filter id 32025            */
+    1,                                      /* encoder present            */
+    1,                                      /* decoder present            */
+    "deltarice",                            /* name (as the reference's)  */
+    NULL,                                   /* can_apply                  */
+    NULL,                                   /* set_local                  */
+    (H5Z_func_t)H5Z_filter_deltarice,
+}};
+
+size_t H5Z_filter_deltarice(unsigned flags, size_t cd_nelmts, const unsigned cd_values[],
+                            size_t nbytes, size_t *buf_size, void **buf)
+{
+    if (!buf || !*buf || !buf_size) return 0;
+    drice_params prm;
+    const int prc = drice_parse_cd_values(cd_nelmts, cd_values, &prm);
+    if (prc != DRICE_OK) {
+        fprintf(stderr, prc == DRICE_E_UNSUPPORTED
+                            ? "deltarice_b200: only the delta pre-filter [1,-1] is implemented on the GPU path\n"
+                            : "deltarice_b200: invalid compression_opts (RiceParameter must be 2^k <= 32768, WaveformLength >= 1 or -1)\n");
+        return 0;
+    }
+    std::lock_guard<std::mutex> lock(g_mu);
+    drice_ctx *ctx = global_ctx();
+    if (!ctx) return 0;
+
+    if (flags & H5Z_FLAG_REVERSE) {
+        if (nbytes < 4 || (nbytes & 3)) {
+            fprintf(stderr, "deltarice_b200: compressed chunk size %zu is not a positive multiple of 4\n", nbytes);
+            return 0;
+        }
+        uint32_t total;
+        memcpy(&total, *buf, 4);
+        if (total > 0x7fffffffu) return 0;
+        const size_t out_bytes = (size_t)total * 2;
+        void *out = malloc(out_bytes ? out_bytes : 1);
+        if (!out) return 0;
+        const uint64_t boff[2] = {0, nbytes};
+        const uint64_t soff[2] = {0, total};
+        const int rc = drice_decode_batch_host(ctx, *buf, boff, 1, soff, prm.M, prm.L, (int16_t *)out);
+        if (rc != DRICE_OK) {
+            fprintf(stderr, "deltarice_b200: de-compression failed: %s\n", drice_last_error(ctx));
+            free(out);
+            return 0;
+        }
+        free(*buf);
+        *buf = out;
+        *buf_size = out_bytes;
+        return out_bytes;
+    }
+
+    if (nbytes & 1) {
+        fprintf(stderr, "deltarice_b200: chunk of %zu bytes is not a whole number of int16 samples\n", nbytes);
+        return 0;
+    }
+    const size_t total = nbytes / 2;
+    if (total > 0x7fffffffull) return 0;
+    const size_t bound = drice_chunk_bound_bytes(total, prm.L);
+    void *out = malloc(bound);
+    if (!out) return 0;
+    const uint64_t soff[2] = {0, total};
+    uint64_t boff[2] = {0, 0};
+    const int rc = drice_encode_batch_host(ctx, (const int16_t *)*buf, soff, 1, prm.M, prm.L, out, bound, boff);
+    if (rc != DRICE_OK) {
+        fprintf(stderr, "deltarice_b200: compression failed: %s\n", drice_last_error(ctx));
+        free(out);
+        return 0;
+    }
+    const size_t used = (size_t)boff[1];
+    if (void *shrunk = realloc(out, used)) out = shrunk;
+    free(*buf);
+    *buf = out;
+    *buf_size = used;
+    return used;
+}
+
+int deltarice_register_h5filter(void)
+{
+    typedef herr_t (*H5Zregister_t)(const void *);
+    H5Zregister_t reg = (H5Zregister_t)dlsym(RTLD_DEFAULT, "H5Zregister");
+    if (!reg) {
+        fprintf(stderr, "deltarice_register_h5filter: no libhdf5 in this process (H5Zregister not found)\n");
+        return -1;
+    }
+    const int retval = reg(H5Z_DELTARICE);
+    if (retval < 0) fprintf(stderr, "deltarice_register_h5filter: can't register deltarice filter\n");
+    return retval;
+}
+
+H5PL_type_t H5PLget_plugin_type(void) { return H5PL_TYPE_FILTER; }
+const void *H5PLget_plugin_info(void) { return H5Z_DELTARICE; }
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+"""CPU suite: the C-ABI library loads, exports every declared symbol and its host-side
+logic (parameter parsing, bounds, error behaviour without a GPU) matches the reference's
+parseCD_VALUES (reference src/deltaRice.c:248-291) and the format's size bound."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import deltarice_b200 as d
+from deltarice_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "deltarice_b200.h")).read()
+    declared = set(re.findall(r"\b(drice_\w+)\s*\(", hdr))
+    declared -= {"drice_ctx"}
+    assert declared == set(_lib.C_ABI_SYMBOLS)
+    for s in list(declared) + _lib.H5_SYMBOLS:
+        assert hasattr(L, s), s
+    assert L.drice_abi_version() == 1
+
+
+def test_h5_class_struct_matches_reference():
+    # reference src/deltaRice.c:19-28: {vers 1, id 32025, enc 1, dec 1, "deltarice", NULL, NULL, filter}
+    L = _lib.load()
+
+    class H5ZClass2(C.Structure):
+        _fields_ = [("version", C.c_int), ("id", C.c_int), ("enc", C.c_uint), ("dec", C.c_uint),
+                    ("name", C.c_char_p), ("can_apply", C.c_void_p), ("set_local", C.c_void_p),
+                    ("filter", C.c_void_p)]
+    cls = H5ZClass2.in_dll(L, "H5Z_DELTARICE")
+    assert (cls.version, cls.id, cls.enc, cls.dec, cls.name) == (1, 32025, 1, 1, b"deltarice")
+    assert cls.can_apply is None and cls.set_local is None
+    assert cls.filter == C.cast(L.H5Z_filter_deltarice, C.c_void_p).value
+    # plugin entry points: type FILTER (0) and info -> the class (reference returns (void*)32025: bug B1)
+    assert L.H5PLget_plugin_type() == 0
+    assert L.H5PLget_plugin_info() == C.addressof(cls)
+
+
+def test_parse_cd_values_defaults_and_forms():
+    assert d.parse_cd_values(()) == (8, -1)
+    assert d.parse_cd_values((16,)) == (16, -1)
+    assert d.parse_cd_values((8, 1024)) == (8, 1024)
+    assert d.parse_cd_values((4, 0xFFFFFFFF)) == (4, -1)
+    assert d.parse_cd_values((8, 1024, 2, 1, 0xFFFFFFFF)) == (8, 1024)   # explicit delta filter
+
+
+@pytest.mark.parametrize("cd", [(0,), (3,), (65536,), (8, 0), (8, 1024, 0), (8, 1024, 2, 1)])
+def test_parse_cd_values_rejects(cd):
+    with pytest.raises(d.DeltaRiceError):
+        d.parse_cd_values(cd)
+
+
+def test_generic_filter_is_refused_not_misencoded():
+    with pytest.raises(d.DeltaRiceError) as e:
+        d.parse_cd_values((8, 1024, 1, 1))
+    assert e.value.code == _lib.E_UNSUPPORTED
+
+
+def test_log2_param():
+    L = _lib.load()
+    for k in range(16):
+        assert L.drice_log2_param(1 << k) == k
+    for M in (0, -4, 3, 12, 1 << 16, 1 << 20):
+        assert L.drice_log2_param(M) == -1
+
+
+def test_bound_matches_oracle(oracle):
+    for total, L in [(0, None), (1, None), (32, None), (7000, 7000), (7001, 7000), (140000, 7000), (100, 7000), (65536, 1024), (50, 1)]:
+        assert d.chunk_bound_bytes(total, L) == 4 * oracle.bound_words(total, L)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(d.DeltaRiceError) as e:
+        d.DeltaRice(0)
+    assert e.value.code == _lib.E_CUDA
+    from deltarice_b200 import h5
+    with pytest.raises(d.DeltaRiceError):
+        h5.apply_filter(np.zeros(64, np.int16).tobytes(), (8, 32))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "deltarice_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f

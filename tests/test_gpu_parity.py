@@ -1,0 +1,179 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the C-ABI (ctypes ->
+libh5deltarice_b200.so), against the oracle on the same seeded inputs.  Bit-exact bar:
+the compressed stream must equal the oracle's byte for byte, decode must reproduce the
+input exactly.  Nothing here reads /root/reference."""
+import os
+
+import numpy as np
+import pytest
+
+from cases import small_cases
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz")
+
+
+def _oracle_batch(oracle, x, off, M, L):
+    parts, boff = [], [0]
+    for c in range(len(off) - 1):
+        s = oracle.encode_chunk(x[int(off[c]):int(off[c + 1])], M, L)
+        parts.append(s)
+        boff.append(boff[-1] + 4 * s.size)
+    return (np.concatenate(parts) if parts else np.zeros(0, np.uint32)), np.array(boff, dtype=np.uint64)
+
+
+@pytest.mark.parametrize("case", small_cases(), ids=lambda c: c[0])
+def test_single_chunk_host_path(codec, oracle, case):
+    name, x, M, L = case
+    x = x.view(np.int16)
+    want = oracle.encode_chunk(x, M, L)
+    got, boff = codec.encode_host(x, None, M, L)
+    assert int(boff[-1]) == 4 * want.size, name
+    assert np.array_equal(got.view(np.uint32), want), name
+    back = codec.decode_host(want.view(np.uint8), None, None, M, L)
+    assert np.array_equal(back, x), name
+
+
+@pytest.mark.parametrize("case", small_cases(), ids=lambda c: c[0])
+def test_single_chunk_h5z_filter(oracle, case):
+    """Through H5Z_filter_deltarice with malloc'ed buffers, as libhdf5 drives it
+    (reference src/deltaRice.c:468-490)."""
+    from deltarice_b200 import h5
+    name, x, M, L = case
+    x = x.view(np.int16)
+    cd = (M,) if L is None else (M, L)
+    stream = h5.apply_filter(x.tobytes(), cd, reverse=False)
+    assert np.array_equal(np.frombuffer(stream, np.uint32), oracle.encode_chunk(x, M, L)), name
+    back = h5.apply_filter(stream, cd, reverse=True)
+    assert np.array_equal(np.frombuffer(back, np.int16), x), name
+
+
+def test_golden_vectors_through_filter():
+    """Streams produced by the UNMODIFIED reference (tests/golden/make_golden.py)."""
+    from deltarice_b200 import h5
+    g = np.load(GOLDEN)
+    for name in g["names"]:
+        x, cd, stream = g[f"{name}__x"], tuple(int(v) for v in g[f"{name}__cd"]), g[f"{name}__stream"]
+        got = h5.apply_filter(x.tobytes(), cd, reverse=False)
+        assert np.array_equal(np.frombuffer(got, np.uint32), stream), name
+        back = h5.apply_filter(stream.tobytes(), cd, reverse=True)
+        assert np.array_equal(np.frombuffer(back, np.int16), x), name
+
+
+def test_readme_config_c1_batch(codec, oracle):
+    """C1: (100,7000) N(0,10), M=8, chunks (20,7000): 5 chunks in ONE launch."""
+    x = np.random.default_rng(0).normal(0, 10, (100, 7000)).astype(np.int16).ravel()
+    off = np.arange(6, dtype=np.uint64) * 140000
+    want, wboff = _oracle_batch(oracle, x, off, 8, 7000)
+    got, boff = codec.encode_host(x, off, 8, 7000)
+    assert np.array_equal(boff, wboff)
+    assert np.array_equal(got.view(np.uint32), want)
+    ratio = got.size / (x.size * 2)
+    assert abs(ratio - 0.405) < 0.002          # 6.48 bits/sample
+    back = codec.decode_host(got, boff, off, 8, 7000)
+    assert np.array_equal(back, x)
+
+
+@pytest.mark.parametrize("M,L", [(8, 7000), (4, 3500), (2, 33), (16, None), (1, 64)])
+def test_ragged_batch_with_empty_chunk(codec, oracle, M, L):
+    r = np.random.default_rng(11)
+    sizes = [7000 * 3, 0, 12345, 1, 7000 * 2 + 1, 3500, 0, 64]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    sig = 1.0 if M == 1 else 30.0
+    x = np.clip(np.rint(r.normal(0, sig, int(off[-1]))), -32768, 32767).astype(np.int16)
+    want, wboff = _oracle_batch(oracle, x, off, M, L)
+    got, boff = codec.encode_host(x, off, M, L)
+    assert np.array_equal(boff, wboff)
+    assert np.array_equal(got.view(np.uint32), want)
+    assert np.array_equal(codec.decode_host(got, boff, off, M, L), x)
+    assert np.array_equal(codec.decode_host(got, boff, None, M, L), x)    # sizes peeked from the stream
+
+
+def test_device_path_unaligned_pointers(codec, oracle):
+    import torch
+    r = np.random.default_rng(21)
+    for shift in (0, 1, 3, 5, 8):
+        for (M, L, n) in [(4, 3500, 3500 * 9), (8, 7000, 7000 * 4 + 17), (8, 1023, 1023 * 11), (2, None, 30000)]:
+            x = np.clip(np.rint(r.normal(0, 25, n)), -32768, 32767).astype(np.int16)
+            buf = torch.zeros(n + 64, dtype=torch.int16, device="cuda")
+            d = buf[shift:shift + n]
+            d.copy_(torch.from_numpy(x))
+            off = np.array([0, n], dtype=np.uint64)
+            cap = codec.bound_bytes(off, L)
+            obuf = torch.zeros(cap + 64, dtype=torch.uint8, device="cuda")
+            o = obuf[4 * (shift % 4):4 * (shift % 4) + cap]
+            comp, boff = codec.encode_device(d, off, M, L, out=o)
+            want = oracle.encode_chunk(x, M, L)
+            assert np.array_equal(comp.cpu().numpy().view(np.uint32), want), (shift, M, L)
+            dec_buf = torch.zeros(n + 64, dtype=torch.int16, device="cuda")
+            dec = codec.decode_device(comp, boff, off, M, L, out=dec_buf[shift:shift + n])
+            assert np.array_equal(dec.cpu().numpy(), x), (shift, M, L)
+            assert int(dec_buf[:shift].abs().sum()) == 0 and int(dec_buf[shift + n:].abs().sum()) == 0
+
+
+def test_many_chunks_many_waves(codec, oracle):
+    """77 chunks x 200 waves of 3500 (Nab-like), M=4: look-back across ~15k waves."""
+    from deltarice_b200.synth import nab_like
+    x = nab_like(77 * 200, 3500, seed=3).ravel()
+    off = np.arange(78, dtype=np.uint64) * (200 * 3500)
+    got, boff = codec.encode_host(x, off, 4, 3500)
+    for c in (0, 1, 38, 76):
+        want = oracle.encode_chunk(x[int(off[c]):int(off[c + 1])], 4, 3500)
+        assert np.array_equal(got[int(boff[c]):int(boff[c + 1])].view(np.uint32), want), c
+    assert np.array_equal(codec.decode_host(got, boff, off, 4, 3500), x)
+
+
+def test_errors(codec, oracle):
+    import deltarice_b200 as d
+    from deltarice_b200 import _lib
+    import ctypes as C
+    x = np.random.default_rng(1).integers(-32768, 32768, 7000).astype(np.int16)
+    off = np.array([0, 7000], dtype=np.uint64)
+    # capacity
+    out = np.empty(1000, dtype=np.uint8)
+    boff = np.zeros(2, dtype=np.uint64)
+    u64p = C.POINTER(C.c_uint64)
+    rc = codec._L.drice_encode_batch_host(codec._h, x.ctypes.data, off.ctypes.data_as(u64p), 1, 8, 7000,
+                                          out.ctypes.data, out.size, boff.ctypes.data_as(u64p))
+    assert rc == _lib.E_CAPACITY
+    # bad M
+    with pytest.raises(d.DeltaRiceError):
+        codec.encode_host(x, off, 12, 7000)
+    # malformed stream: truncated record, wrong count, wrong expected size
+    s = oracle.encode_chunk(x, 8, 7000)
+    with pytest.raises(d.DeltaRiceError):
+        codec.decode_host(s[:-3].view(np.uint8), None, None, 8, 7000)
+    bad = s.copy()
+    bad[1] += 5
+    with pytest.raises(d.DeltaRiceError):
+        codec.decode_host(bad.view(np.uint8), None, None, 8, 7000)
+    with pytest.raises(d.DeltaRiceError):
+        codec.decode_host(s.view(np.uint8), None, np.array([0, 6999], dtype=np.uint64), 8, 7000)
+    # the context stays usable after errors
+    assert np.array_equal(codec.decode_host(s.view(np.uint8), None, None, 8, 7000), x)
+
+
+def test_full_size_c2_roundtrip_and_sampled_parity(codec, oracle):
+    """BASELINE config C2 at full size (153 391 Nab-like waves of 3500, M=4, ~1 GB): device
+    round trip decode(encode(x)) == x, compression ratio, and byte parity with the oracle on
+    sampled chunks."""
+    import torch
+    from deltarice_b200.synth import nab_like_torch
+    n_waves, L, M, wpc = 153391, 3500, 4, 2000
+    x = nab_like_torch(n_waves, L, 20251018, "cuda").reshape(-1)
+    from deltarice_b200 import chunk_offsets
+    off = chunk_offsets(wpc * L, x.numel())
+    comp, boff = codec.encode_device(x, off, M, L)
+    ratio = comp.numel() / (x.numel() * 2)
+    assert 0.22 < ratio < 0.32, ratio
+    y = codec.decode_device(comp, boff, off, M, L)
+    assert torch.equal(x, y)
+    for c in (0, 37, len(off) - 2):
+        xs = x[int(off[c]):int(off[c + 1])].cpu().numpy()
+        want = oracle.encode_chunk(xs, M, L, mt=True)
+        got = comp[int(boff[c]):int(boff[c + 1])].cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, want), c
+    # size-independent property: total bytes = 4*(chunks + waves + sum nwords) and every chunk
+    # stream starts with its sample count
+    heads = comp.view(torch.int32)[torch.from_numpy((boff[:-1] // 4).astype(np.int64)).cuda()]
+    assert torch.equal(heads.cpu(), torch.from_numpy(np.diff(off).astype(np.int32)))
