@@ -34,6 +34,7 @@ C_ABI_SYMBOLS = [
     "drice_host_alloc", "drice_host_free", "drice_encode_batch_dev_async", "drice_encode_batch_dev",
     "drice_decode_batch_dev_async", "drice_decode_batch_dev", "drice_encode_batch_host",
     "drice_decode_batch_host", "drice_peek_chunk_samples", "drice_launch_count",
+    "drice_timing_enable", "drice_timing_read", "drice_kernel_name",
 ]
 H5_SYMBOLS = ["H5Z_DELTARICE", "H5Z_filter_deltarice", "deltarice_register_h5filter",
               "H5PLget_plugin_type", "H5PLget_plugin_info"]
@@ -88,6 +89,12 @@ def load() -> C.CDLL:
     L.drice_peek_chunk_samples.argtypes = [vp, u64p, sz, u64p]
     L.drice_launch_count.restype = C.c_uint64
     L.drice_launch_count.argtypes = [vp]
+    L.drice_timing_enable.restype = i
+    L.drice_timing_enable.argtypes = [vp, i]
+    L.drice_timing_read.restype = i
+    L.drice_timing_read.argtypes = [vp, C.POINTER(C.c_double), u64p, i]
+    L.drice_kernel_name.restype = C.c_char_p
+    L.drice_kernel_name.argtypes = [i]
     L.H5Z_filter_deltarice.restype = sz
     L.H5Z_filter_deltarice.argtypes = [C.c_uint, sz, C.POINTER(C.c_uint), sz, C.POINTER(sz), C.POINTER(vp)]
     L.deltarice_register_h5filter.restype = i

@@ -72,12 +72,16 @@ class DeltaRice:
         if rc != 0:
             raise DeltaRiceError(rc, (self._L.drice_last_error(None) or b"").decode())
         self._h = h
+        self._pinned = []
         self.device = int(self._L.drice_device(h))
 
     def close(self):
         if getattr(self, "_h", None):
             self._L.drice_destroy(self._h)
             self._h = None
+            for p in self._pinned:
+                self._L.drice_host_free(p)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -99,6 +103,29 @@ class DeltaRice:
     def launches(self) -> int:
         return int(self._L.drice_launch_count(self._h))
 
+    def timing(self, on: bool = True):
+        """Bracket every kernel launch with CUDA events (bench.py's roofline leg)."""
+        self._check(self._L.drice_timing_enable(self._h, 1 if on else 0))
+
+    def timing_read(self, reset: bool = True) -> dict:
+        """{kernel name: (summed ms, launches)} since the last reset; waits for pending events."""
+        n = 3
+        ms = (C.c_double * n)()
+        cnt = (C.c_uint64 * n)()
+        self._check(self._L.drice_timing_read(self._h, ms, cnt, 1 if reset else 0))
+        return {self._L.drice_kernel_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n)}
+
+    def pinned_empty(self, n: int, dtype) -> np.ndarray:
+        """numpy array over page-locked host memory (drice_host_alloc); freed with the codec."""
+        dt = np.dtype(dtype)
+        nbytes = max(1, int(n) * dt.itemsize)
+        p = self._L.drice_host_alloc(nbytes)
+        if not p:
+            raise DeltaRiceError(_lib.E_NOMEM, "drice_host_alloc failed")
+        self._pinned.append(p)
+        buf = (C.c_uint8 * nbytes).from_address(p)
+        return np.frombuffer(buf, dtype=dt, count=int(n))
+
     def bound_bytes(self, sample_off, L=None) -> int:
         off = _u64(sample_off)
         return int(self._L.drice_batch_bound_bytes(_p(off), off.size - 1, _Lval(L)))
@@ -118,6 +145,18 @@ class DeltaRice:
         self._check(self._L.drice_encode_batch_host(self._h, raw.ctypes.data, _p(off), n, int(M), _Lval(L),
                                                     out.ctypes.data, cap, _p(boff)))
         return out[: int(boff[-1])], boff
+
+    def encode_host_into(self, raw: np.ndarray, sample_off, M: int, L, out: np.ndarray, boff: np.ndarray) -> int:
+        """As encode_host, into caller buffers (e.g. pinned_empty); returns the stream's bytes."""
+        off = _u64(sample_off)
+        self._check(self._L.drice_encode_batch_host(self._h, raw.ctypes.data, _p(off), off.size - 1, int(M), _Lval(L),
+                                                    out.ctypes.data, out.nbytes, _p(boff)))
+        return int(boff[off.size - 1])
+
+    def decode_host_into(self, comp: np.ndarray, byte_off, sample_off, M: int, L, out: np.ndarray) -> None:
+        boff, off = _u64(byte_off), _u64(sample_off)
+        self._check(self._L.drice_decode_batch_host(self._h, comp.ctypes.data, _p(boff), boff.size - 1, _p(off),
+                                                    int(M), _Lval(L), out.ctypes.data))
 
     def decode_host(self, comp: np.ndarray, byte_off=None, sample_off=None, M: int = 8, L=None) -> np.ndarray:
         comp = np.ascontiguousarray(comp).view(np.uint8).reshape(-1)
@@ -140,7 +179,10 @@ class DeltaRice:
     @staticmethod
     def _stream():
         import torch
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        h = torch.cuda.current_stream().cuda_stream
+        # torch's default stream is the legacy NULL stream; NULL means "the context's own
+        # stream" in the C-ABI, so name the legacy stream explicitly (cudaStreamLegacy == 1)
+        return C.c_void_p(h if h else 1)
 
     def encode_device(self, raw, sample_off=None, M: int = 8, L=None, out=None):
         """torch int16 CUDA tensor -> (torch uint8 CUDA tensor [valid bytes], byte offsets ndarray)."""

@@ -58,6 +58,14 @@ struct drice_ctx {
     std::string err;
     uint64_t launches = 0;
 
+    // optional per-kernel timing (drice_timing_*): event pairs recorded around launches
+    bool timing = false;
+    struct TimedLaunch { int kind; cudaEvent_t e0, e1; };
+    std::vector<TimedLaunch> timed;             // pending, not yet resolved
+    std::vector<cudaEvent_t> ev_pool;
+    double   t_ms[DRICE_NUM_KERNELS] = {0, 0, 0};
+    uint64_t t_n[DRICE_NUM_KERNELS] = {0, 0, 0};
+
     // per-call tables (host pinned staging + device)
     void  *h_tab = nullptr;
     size_t h_tab_cap = 0;
@@ -167,6 +175,39 @@ int upload_tables(drice_ctx *ctx, const uint64_t *t0, const uint64_t *t1, const 
     *d_w = (uint32_t *)((char *)ctx->d_tab.p + n1 * 16);
     return DRICE_OK;
 }
+
+cudaEvent_t timing_event(drice_ctx *ctx)
+{
+    if (!ctx->ev_pool.empty()) {
+        cudaEvent_t e = ctx->ev_pool.back();
+        ctx->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// brackets one kernel launch with events on its stream when timing is on
+struct TimedScope {
+    drice_ctx *ctx;
+    cudaStream_t st;
+    int kind;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    TimedScope(drice_ctx *c, int k, cudaStream_t s) : ctx(c), st(s), kind(k)
+    {
+        if (!ctx->timing) return;
+        e0 = timing_event(ctx);
+        e1 = timing_event(ctx);
+        if (e0) cudaEventRecord(e0, st);
+    }
+    ~TimedScope()
+    {
+        if (!ctx->timing) return;
+        if (e1) cudaEventRecord(e1, st);
+        if (e0 && e1) ctx->timed.push_back({kind, e0, e1});
+    }
+};
 
 int status_to_error(drice_ctx *ctx, uint32_t status)
 {
@@ -285,6 +326,8 @@ extern "C" void drice_destroy(drice_ctx *ctx)
         if (s.ev_out) cudaEventDestroy(s.ev_out);
         if (s.h_offs_pinned) cudaFreeHost(s.h_offs_pinned);
     }
+    for (auto &t : ctx->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     ctx->d_tab.release(); ctx->d_scratch.release(); ctx->d_offs.release();
     if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
     if (ctx->h_sync) cudaFreeHost(ctx->h_sync);
@@ -298,6 +341,41 @@ extern "C" void drice_destroy(drice_ctx *ctx)
 extern "C" const char *drice_last_error(const drice_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 extern "C" int drice_device(const drice_ctx *ctx) { return ctx ? ctx->device : -1; }
 extern "C" uint64_t drice_launch_count(const drice_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int drice_timing_enable(drice_ctx *ctx, int on)
+{
+    if (!ctx) return DRICE_E_PARAM;
+    ctx->timing = on != 0;
+    return DRICE_OK;
+}
+
+extern "C" int drice_timing_read(drice_ctx *ctx, double *ms, uint64_t *launches, int reset)
+{
+    if (!ctx) return DRICE_E_PARAM;
+    DR_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (auto &t : ctx->timed) {
+        DR_CUDA(ctx, cudaEventSynchronize(t.e1));
+        float f = 0.f;
+        DR_CUDA(ctx, cudaEventElapsedTime(&f, t.e0, t.e1));
+        ctx->t_ms[t.kind] += f;
+        ctx->t_n[t.kind] += 1;
+        ctx->ev_pool.push_back(t.e0);
+        ctx->ev_pool.push_back(t.e1);
+    }
+    ctx->timed.clear();
+    for (int k = 0; k < DRICE_NUM_KERNELS; ++k) {
+        if (ms) ms[k] = ctx->t_ms[k];
+        if (launches) launches[k] = ctx->t_n[k];
+        if (reset) { ctx->t_ms[k] = 0; ctx->t_n[k] = 0; }
+    }
+    return DRICE_OK;
+}
+
+extern "C" const char *drice_kernel_name(int kind)
+{
+    static const char *names[DRICE_NUM_KERNELS] = {"encode_kernel", "locate_kernel", "parse_kernel"};
+    return (kind >= 0 && kind < DRICE_NUM_KERNELS) ? names[kind] : nullptr;
+}
 
 extern "C" void *drice_host_alloc(size_t bytes)
 {
@@ -357,7 +435,11 @@ extern "C" int drice_encode_batch_dev_async(drice_ctx *ctx, const int16_t *d_raw
     p.uniform_wpc = g.uniform_wpc;
     p.L = g.Lk;
     p.k = k;
-    int nl = launch_encode(p, g.max_wave, st);
+    int nl;
+    {
+        TimedScope ts(ctx, DRICE_KERNEL_ENCODE, st);
+        nl = launch_encode(p, g.max_wave, st);
+    }
     if (nl < 0) return fail(ctx, DRICE_E_PARAM, "unsupported RiceParameter");
     ctx->launches += (uint64_t)nl;
     DR_CUDA(ctx, cudaGetLastError());
@@ -450,7 +532,10 @@ extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_co
     lp.status = d_status;
     lp.nchunks = (uint32_t)nchunks;
     lp.L = g.Lk;
-    ctx->launches += (uint64_t)launch_locate(lp, st);
+    {
+        TimedScope ts(ctx, DRICE_KERNEL_LOCATE, st);
+        ctx->launches += (uint64_t)launch_locate(lp, st);
+    }
 
     ParseParams pp{};
     pp.comp = d_comp;
@@ -464,7 +549,11 @@ extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_co
     pp.max_n = g.max_wave;
     pp.k = k;
     const bool wide = g.wave_offsets_mult4 && (reinterpret_cast<uintptr_t>(d_out) & 7) == 0;
-    int nl = launch_parse(pp, wide ? 8 : 2, st);
+    int nl;
+    {
+        TimedScope ts(ctx, DRICE_KERNEL_PARSE, st);
+        nl = launch_parse(pp, wide ? 8 : 2, st);
+    }
     if (nl < 0) return fail(ctx, DRICE_E_PARAM, "unsupported RiceParameter");
     ctx->launches += (uint64_t)nl;
     DR_CUDA(ctx, cudaGetLastError());

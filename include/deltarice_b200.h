@@ -142,6 +142,19 @@ DRICE_API int drice_peek_chunk_samples(const void *h_comp, const uint64_t *chunk
 /* Number of kernels the context has launched so far (bench.py's gpu_launches). */
 DRICE_API uint64_t drice_launch_count(const drice_ctx *ctx);
 
+/* Per-kernel device timing (bench.py's roofline leg).  While enabled every kernel launch is
+ * bracketed by a pair of CUDA events on the stream it is launched on.  drice_timing_read
+ * waits for the pending events and returns, per kernel kind, the summed duration in
+ * milliseconds and the number of launches since the last reset. */
+#define DRICE_KERNEL_ENCODE 0
+#define DRICE_KERNEL_LOCATE 1
+#define DRICE_KERNEL_PARSE  2
+#define DRICE_NUM_KERNELS   3
+DRICE_API int drice_timing_enable(drice_ctx *ctx, int on);
+DRICE_API int drice_timing_read(drice_ctx *ctx, double *ms /* [DRICE_NUM_KERNELS] */,
+                      uint64_t *launches /* [DRICE_NUM_KERNELS] */, int reset);
+DRICE_API const char *drice_kernel_name(int kind);
+
 #ifdef __cplusplus
 }
 #endif
