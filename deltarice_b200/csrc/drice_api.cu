@@ -109,6 +109,7 @@ struct Geometry {
     uint32_t max_wave = 0;
     uint32_t Lk = 0;                   // kernel L (0 = whole chunk)
     bool     wave_offsets_mult4 = true;
+    uint32_t align_samples = 8;        // largest power of two <= 8 dividing every wave start and end
 };
 
 int build_geometry(drice_ctx *ctx, const uint64_t *off, size_t nchunks, int64_t L, bool encode, Geometry &g)
@@ -121,6 +122,7 @@ int build_geometry(drice_ctx *ctx, const uint64_t *off, size_t nchunks, int64_t 
     uint64_t nw = 0;
     bool uniform = true;
     uint64_t first_w = 0;
+    uint64_t align_bits = off[nchunks] | 8;
     for (size_t c = 0; c < nchunks; ++c) {
         if (off[c + 1] < off[c]) return fail(ctx, DRICE_E_PARAM, "chunk_sample_off must be non-decreasing");
         const uint64_t total = off[c + 1] - off[c];
@@ -130,7 +132,10 @@ int build_geometry(drice_ctx *ctx, const uint64_t *off, size_t nchunks, int64_t 
         uint64_t w = total ? (total + Lw - 1) / Lw : 0;
         if (encode && total == 0) w = 1;      // pseudo wave: emits the [0] chunk header
         g.wave_off[c] = (uint32_t)nw;
-        if (c == 0) first_w = w; else if (w != first_w) uniform = false;
+        // every chunk but the last must hold the same number of waves for wave -> chunk by division
+        if (c == 0) first_w = w; else if (w != first_w && !(c + 1 == nchunks && w <= first_w)) uniform = false;
+        align_bits |= off[c];
+        if (w > 1) align_bits |= Lw;
         nw += w;
         if (nw > 0xfffffff0ull) return fail(ctx, DRICE_E_PARAM, "too many waves in one batch");
         g.max_wave = std::max<uint32_t>(g.max_wave, (uint32_t)std::min<uint64_t>(Lw, total));
@@ -139,6 +144,7 @@ int build_geometry(drice_ctx *ctx, const uint64_t *off, size_t nchunks, int64_t 
     g.wave_off[nchunks] = (uint32_t)nw;
     g.nwaves = (uint32_t)nw;
     g.uniform_wpc = (uniform && nchunks > 0 && first_w > 0) ? (uint32_t)first_w : 0u;
+    g.align_samples = (uint32_t)(align_bits & (~align_bits + 1));
     return DRICE_OK;
 }
 
@@ -414,10 +420,12 @@ extern "C" int drice_encode_batch_dev_async(drice_ctx *ctx, const int16_t *d_raw
     uint32_t *d_woff;
     rc = upload_tables(ctx, off, nullptr, g.wave_off.data(), nchunks, st, &d_soff, &d_unused, &d_woff);
     if (rc) return rc;
-    const size_t scratch = (size_t)g.nwaves * 8 + 16;
+    // scratch: [ticket u32][pad] | look-back status u64 per tile (at most one per wave), zeroed
+    const size_t zeroed = (size_t)g.nwaves * 8 + 16;
+    const size_t scratch = zeroed;
     if (scratch > ctx->d_scratch.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
     DR_CUDA(ctx, ctx->d_scratch.reserve(scratch));
-    DR_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch.p, 0, scratch, st));
+    DR_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch.p, 0, zeroed, st));
 
     EncodeParams p{};
     p.raw = d_raw;

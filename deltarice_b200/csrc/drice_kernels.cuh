@@ -16,8 +16,10 @@ namespace drice {
 constexpr int      kSamplesPerThread = 16;   // one 32-byte aligned slot per thread
 constexpr uint32_t kEscapeQuotient   = 8;    // reference "giveup", src/deltaRice.c:203
 constexpr uint32_t kEscapeBits       = 25;   // 8 zeros + 1 + 16 value bits
-constexpr int      kEncMaxThreads    = 512;  // single-tile encoder: L <= 512*16-15
-constexpr int      kEncTileMaxL      = kEncMaxThreads * kSamplesPerThread - (kSamplesPerThread - 1);
+constexpr int      kEncMaxThreads    = 512;  // CTA size of the long-wave / redo kernels
+constexpr int      kEncWarps         = 8;    // worker warps per CTA of the tile kernel (+1 control warp)
+constexpr int      kEncWavesPerWarp  = 1;    // waves per worker warp and tile
+constexpr int      kEncTileMaxL      = 8192; // longest wave the warp-per-wave kernel takes
 
 // status flags
 constexpr uint32_t kErrCapacity = 1u;   // output capacity exceeded
@@ -32,7 +34,7 @@ struct EncodeParams {
     const uint64_t *chunk_sample_off;   // [nchunks+1]
     const uint32_t *chunk_wave_off;     // [nchunks+1]
     uint64_t       *chunk_byte_off;     // [nchunks+1] result (BYTE offsets of the chunk streams)
-    uint64_t       *lookback;           // [nwaves], zeroed
+    uint64_t       *lookback;           // [ntiles] (<= nwaves), zeroed
     uint32_t       *ticket;             // zeroed
     uint32_t       *status;             // error flags (OR-ed)
     uint32_t        nchunks;
