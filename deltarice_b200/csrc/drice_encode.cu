@@ -136,6 +136,31 @@ __device__ __forceinline__ void rice_code(uint32_t u, uint32_t &val, uint32_t &l
 
 // window state of the packer: `lo` holds the pending bits in its low `n` (< 32) bits; any
 // bits above them are stale and never looked at (words are cut out with funnel shifts)
+// a register holding a compile-time constant the compiler cannot see through: keeps
+// (u | c1) & c2 one three-register LOP3 instead of two immediate forms
+__device__ __forceinline__ uint32_t opaque(uint32_t c)
+{
+    uint32_t r;
+    asm("mov.u32 %0, %1;" : "=r"(r) : "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul_wide(uint32_t a, uint32_t b)
+{
+    uint64_t d;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(d) : "r"(a), "r"(b));
+    return d;
+}
+
+// Bit packer of one lane.  `lo` holds the pending bits in its low `n` (< 32) bits; bits above
+// them are stale and never looked at (finished words are cut out with funnel shifts).
+// Appending a code is lo * 2^len | value in a 64-bit window: the multiply is the shift and
+// runs on the FMA pipe (IMAD.WIDE), off the busier ALU pipe.
 template <bool kGuard>
 struct Packer {
     uint32_t lo, n;
@@ -146,56 +171,27 @@ struct Packer {
     {
         if (!kGuard || q < end) *q = v;
     }
-
-    // append one code of len <= 31 bits
+    // append one code of len <= 31 bits (value < 2^len)
     __device__ __forceinline__ void put(uint32_t v, uint32_t len)
     {
-        const uint64_t a = mad_wide(lo, pow2(len), (uint64_t)v);
+        const uint64_t a = mul_wide(lo, pow2(len));
+        const uint32_t alo = (uint32_t)a | v;            // the low `len` bits of the product are 0
         n += len;
         if (n >= 32u) {
             n -= 32u;
-            store(ptr++, __funnelshift_r((uint32_t)a, (uint32_t)(a >> 32), n));
+            store(ptr++, __funnelshift_r(alo, (uint32_t)(a >> 32), n));
         }
-        lo = (uint32_t)a;
-    }
-    // append two codes of len <= 31 bits each with one flush of up to two words
-    __device__ __forceinline__ void put2(uint32_t vA, uint32_t lenA, uint32_t vB, uint32_t lenB)
-    {
-        const uint32_t eB = pow2(lenB);
-        const uint64_t a = mad_wide(lo, pow2(lenA), (uint64_t)vA);
-        const uint64_t r10 = mad_wide((uint32_t)a, eB, (uint64_t)vB);
-        const uint64_t r21 = mad_wide((uint32_t)(a >> 32), eB, r10 >> 32);
-        const uint32_t r0 = (uint32_t)r10, r1 = (uint32_t)r21, r2 = (uint32_t)(r21 >> 32);
-        n += lenA + lenB;
-        const uint32_t k = n >> 5;                       // 0, 1 or 2 finished words
-        const uint32_t X = __funnelshift_r(r1, r2, n), Y = __funnelshift_r(r0, r1, n);
-        if (k == 2u) store(ptr, X);
-        ptr += k;
-        if (k != 0u) store(ptr - 1, Y);
-        n &= 31u;
-        lo = r0;
+        lo = alo;
     }
 };
 
 // 16 consecutive samples of one lane as 8 packed words.  `q` = address of the lane's first
 // sample; the widest naturally aligned vector load the wave's start allows is used (warp
-// uniform `mis` = (address of the wave's first sample mod 16) / 2).  `edge`: the slot may
-// leave the batch buffer [.., hi): read element-wise.
+// uniform `mis` = (address of the wave's first sample mod 16) / 2).
 struct RawWords { uint32_t w[8]; };
 
-__device__ __forceinline__ RawWords load_round(const int16_t *q, uint32_t mis, bool active, bool edge,
-                                               const int16_t *hi)
+__device__ __forceinline__ void load_slot(RawWords &r, const int16_t *q, uint32_t mis)
 {
-    RawWords r;
-#pragma unroll
-    for (int m = 0; m < 8; ++m) r.w[m] = 0;
-    if (!active) return r;
-    if (edge && q + S > hi) {
-#pragma unroll
-        for (int i = 0; i < S; ++i)
-            if (q + i < hi) r.w[i >> 1] |= (uint32_t)(uint16_t)q[i] << (16 * (i & 1));
-        return r;
-    }
     if (mis == 0) {
         const uint4 a = __ldg(reinterpret_cast<const uint4 *>(q)), b = __ldg(reinterpret_cast<const uint4 *>(q) + 1);
         r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w;
@@ -220,11 +216,22 @@ __device__ __forceinline__ RawWords load_round(const int16_t *q, uint32_t mis, b
 #pragma unroll
         for (int v = 0; v < 8; ++v) r.w[v] = prmt(t[v], t[v + 1], 0x5432);
     }
-    return r;
+}
+// slot that may be short or leave the batch buffer [.., hi): `nvalid` samples, rest zero
+__device__ __forceinline__ void load_slot_tail(RawWords &r, const int16_t *q, uint32_t mis, uint32_t nvalid,
+                                               const int16_t *hi)
+{
+#pragma unroll
+    for (int m = 0; m < 8; ++m) r.w[m] = 0;
+    if (nvalid == 0) return;
+    if (q + S <= hi) { load_slot(r, q, mis); return; }
+#pragma unroll
+    for (int i = 0; i < S; ++i)
+        if (q + i < hi) r.w[i >> 1] |= (uint32_t)(uint16_t)q[i] << (16 * (i & 1));
 }
 
-// exclusive word offset of tile g among all tiles: decoupled look-back by one warp, four
-// rows of 32 status words in flight per round trip
+// exclusive word offset of tile g among all tiles: decoupled look-back by one warp, four rows of
+// 32 status words in flight per round trip.  The tile's own aggregate is already published.
 __device__ __forceinline__ uint64_t lookback_excl(uint64_t *lookback, uint32_t g, uint64_t mine, int lane)
 {
     uint64_t excl = 0;
@@ -256,70 +263,15 @@ __device__ __forceinline__ uint64_t lookback_excl(uint64_t *lookback, uint32_t g
                         done = pm != 0;
                         break;
                     }
-                    __nanosleep(100);
+                    __nanosleep(200);
                     if ((v >> 62) == 0) v = ld_relaxed_u64(lookback + my);
                 }
             }
             idx -= 128;
         }
-        if (lane == 0) st_relaxed_u64(lookback + g, kFlagPrefix | (excl + mine));
     }
+    if (lane == 0) st_relaxed_u64(lookback + g, kFlagPrefix | (excl + mine));
     return excl;
-}
-
-// per-wave addressing
-struct WaveView {
-    const int16_t *wave, *raw_hi;
-    uint32_t mis;               // (address of the first sample mod 16) / 2
-    uint32_t n, nrounds;
-    bool edge_hi;               // slots of the last round can leave the batch buffer
-
-    __device__ __forceinline__ WaveView(const EncodeParams &p, const WaveGeom &wg)
-    {
-        wave = p.raw + wg.begin;
-        raw_hi = p.raw + p.raw_samples;
-        mis = (uint32_t)((reinterpret_cast<uintptr_t>(wave) & 15u) >> 1);
-        n = wg.n;
-        nrounds = (n + kRound - 1) / kRound;
-        edge_hi = wave + (size_t)nrounds * kRound > raw_hi;
-    }
-    __device__ __forceinline__ RawWords load(uint32_t r, int lane) const
-    {
-        const uint32_t s0 = r * kRound + lane * S;
-        return load_round(wave + s0, mis, s0 < n, r + 1 == nrounds && edge_hi, raw_hi);
-    }
-};
-
-// packed words of one lane and round -> packed zig-zag values; `prev_last` carries the last
-// word of the previous round's lane 31 (0 at the start of a wave: d[0] = x[0], :53-56)
-__device__ __forceinline__ void delta_zigzag(uint32_t (&w)[8], uint32_t nvalid, uint32_t &prev_last, int lane,
-                                             uint32_t (&U)[8], uint32_t &uor)
-{
-    // short last slot: repeat the last valid sample; its codes (delta 0) trail the lane's bits
-    // and are cut off by the callers
-    if (nvalid > 0 && nvalid < (uint32_t)S) {
-#pragma unroll
-        for (int v = 0; v < 8; ++v) {
-            if (2u * v + 1 == nvalid) w[v] = prmt(w[v], 0, 0x1010);
-            if (v > 0 && 2u * v >= nvalid) w[v] = prmt(w[v - 1], 0, 0x3232);
-        }
-    }
-    // word holding the sample before this lane's first one in its HIGH half
-    uint32_t pw = __shfl_up_sync(0xffffffffu, w[7], 1);
-    if (lane == 0) pw = prev_last;
-    prev_last = __shfl_sync(0xffffffffu, w[7], 31);
-    // D = per-half (x[j] - x[j-1]);  U = (D + D) ^ sign(D)   (src/deltaRice.c:57-62, :207-211)
-    uor = 0;
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const uint32_t prev = m ? w[m - 1] : pw;
-        const uint32_t X = w[m] * 0xFFFF0001u;              // high half: hi(w) - lo(w)
-        const uint32_t Y = w[m] - (prev >> 16);             // low half:  lo(w) - hi(prev)
-        const uint32_t D = prmt(Y, X, 0x7610);
-        const uint32_t Sg = prmt(D, 0, 0xbb99);             // per-half sign mask
-        U[m] = __vadd2(D, D) ^ Sg;
-        uor |= U[m];
-    }
 }
 
 template <int K>
@@ -330,50 +282,75 @@ struct RiceConst {
     static constexpr uint32_t HM = ((0xFFFFu << ((K + 3) > 16 ? 16 : (K + 3))) & 0xFFFFu) * 0x10001u;   // quotient >= 8
 };
 
-// encoding sweep.  kDirect = false: packs into the warp's staging of `cap` words; when the wave
-// outgrows it, packing stops (sizing continues) and *overflow is set.  kDirect = true: packs
-// straight into the record in HBM, `cap` = the wave's word count (nothing is stored past it).
-// Returns the wave's bit count.
-template <int K, bool kDirect>
-__device__ __forceinline__ uint32_t encode_wave(const WaveView &wv, int lane, uint32_t *dst, uint32_t cap, bool *overflow)
+// state of one wave's encoding sweep (warp uniform unless noted)
+struct SweepState {
+    uint32_t base;          // bits packed so far
+    uint32_t carry_round;   // pending bits (left aligned) of the previous round's last lane
+    uint32_t prev_last;     // last packed word of the previous round's lane 31
+    bool     ovf;           // staging overflowed: sizing only from here on
+};
+
+// One round = 512 samples = 16 per lane.  kFull: every lane holds 16 valid samples.
+template <int K, bool kDirect, bool kFull>
+__device__ __forceinline__ void encode_round(RawWords &cur, uint32_t nvalid, bool last_lane, int lane,
+                                             uint32_t *dst, uint32_t cap, SweepState &st)
 {
-    bool ovf = false;
     using C = RiceConst<K>;
     constexpr bool kPairs = C::kPairs;
     constexpr uint32_t M = C::M;
-    uint32_t base = 0;                  // bits packed so far
-    uint32_t carry_round = 0;           // pending bits (left aligned) of the previous round's last lane
-    uint32_t prev_last = 0;
-    RawWords cur = wv.load(0, lane);
-    for (uint32_t r = 0; r < wv.nrounds; ++r) {
-        const uint32_t s0 = r * kRound + lane * S;
-        const int32_t rem = (int32_t)wv.n - (int32_t)s0;
-        const uint32_t nvalid = rem >= S ? (uint32_t)S : (rem > 0 ? (uint32_t)rem : 0u);
-        RawWords nxt = cur;
-        if (r + 1 < wv.nrounds) nxt = wv.load(r + 1, lane);
-        uint32_t U[8], uor;
-        delta_zigzag(cur.w, nvalid, prev_last, lane, U, uor);
-
-        // ---- Rice codes: items (value, length) kept in registers across the scan ---------
-        // kPairs: item m = samples 2m, 2m+1 merged into one code of <= 30 bits; an item that
-        // holds an escape is flagged (bit 7 of its length) and keeps the packed zig-zag
-        // values instead.  !kPairs: 16 single-sample items.
-        constexpr int NI = kPairs ? 8 : S;
-        uint32_t iv[NI], il[NI];
-        uint32_t T = 0;                     // bits of this lane
-        bool flagged = false;
-        if (kPairs) {
+    uint32_t (&w)[8] = cur.w;
+    // short last slot: repeat the last valid sample; its codes (delta 0) trail the lane's bits
+    // and are cut off below
+    if (!kFull && nvalid > 0 && nvalid < (uint32_t)S) {
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const uint32_t u2 = U[m];
-                const uint32_t V2 = (u2 | C::MM) & C::NN;
-                const uint32_t qhi = u2 >> (16 + K), qlo = (u2 >> K) & C::QM;
-                il[m] = qlo + qhi + 2u * (K + 1);
-                iv[m] = (V2 & 0xFFFFu) * ((2u * M) << qhi) + (V2 >> 16);
-                T += il[m];
-            }
-            flagged = (uor & C::HM) != 0u;
-            if (flagged) {                  // rare and divergent: redo the items that hold an escape
+        for (int v = 0; v < 8; ++v) {
+            if (2u * v + 1 == nvalid) w[v] = prmt(w[v], 0, 0x1010);
+            if (v > 0 && 2u * v >= nvalid) w[v] = prmt(w[v - 1], 0, 0x3232);
+        }
+    }
+    // word holding the sample before this lane's first one in its HIGH half
+    uint32_t pw = __shfl_up_sync(0xffffffffu, w[7], 1);
+    if (lane == 0) pw = st.prev_last;
+    st.prev_last = __shfl_sync(0xffffffffu, w[7], 31);
+
+    // ---- delta + zig-zag on packed halves: D = per-half (x[j] - x[j-1]);  U = (D + D) ^ sign(D)
+    // (src/deltaRice.c:57-62, :207-211)
+    uint32_t U[8];
+    uint32_t uor = 0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const uint32_t prev = m ? w[m - 1] : pw;
+        const uint32_t X = w[m] * 0xFFFF0001u;              // high half: hi(w) - lo(w)
+        const uint32_t Y = w[m] - (prev >> 16);             // low half:  lo(w) - hi(prev)
+        const uint32_t D = prmt(Y, X, 0x7610);
+        const uint32_t Sg = prmt(D, 0, 0xbb99);             // per-half sign mask
+        U[m] = __vadd2(D, D) ^ Sg;
+        uor |= U[m];
+    }
+
+    // ---- Rice codes: items (value, length) kept in registers across the scan ---------------
+    // kPairs: item m = samples 2m, 2m+1 merged into one code of <= 30 bits; an item that holds
+    // an escape is flagged (bit 7 of its length) and keeps the packed zig-zag values instead.
+    // !kPairs: 16 single-sample items.
+    constexpr int NI = kPairs ? 8 : S;
+    uint32_t iv[NI], il[NI];
+    uint32_t T = 0;                     // bits of this lane
+    bool any_flag = false;              // warp uniform: some lane holds an escape
+    if (kPairs) {
+        const uint32_t MMr = opaque(C::MM), NNr = opaque(C::NN);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const uint32_t u2 = U[m];
+            const uint32_t V2 = (u2 | MMr) & NNr;
+            const uint32_t qhi = u2 >> (16 + K), qlo = (u2 >> K) & C::QM;
+            il[m] = qlo + qhi + 2u * (K + 1);
+            iv[m] = mad_lo(V2 & 0xFFFFu, (2u * M) << qhi, V2 >> 16);
+        }
+        T = ((il[0] + il[1]) + (il[2] + il[3])) + ((il[4] + il[5]) + (il[6] + il[7]));
+        const bool flagged = (uor & C::HM) != 0u;
+        any_flag = __any_sync(0xffffffffu, flagged);
+        if (any_flag) {                 // rare: redo the items that hold an escape
+            if (flagged) {
 #pragma unroll
                 for (int m = 0; m < 8; ++m) {
                     if (U[m] & C::HM) {
@@ -386,134 +363,176 @@ __device__ __forceinline__ uint32_t encode_wave(const WaveView &wv, int lane, ui
                     }
                 }
             }
-            // padding samples of a short last slot were coded as delta 0: K+1 bits each
-            if (nvalid < (uint32_t)S) T = nvalid ? T - ((uint32_t)S - nvalid) * (K + 1) : 0u;
-        } else {
-#pragma unroll
-            for (int j = 0; j < S; ++j) {
-                const uint32_t u = (j & 1) ? (U[j >> 1] >> 16) : (U[j >> 1] & 0xFFFFu);
-                rice_code<K>(u, iv[j], il[j]);
-                if ((uint32_t)j >= nvalid) { iv[j] = 0; il[j] = 0; }
-                T += il[j];
-            }
         }
-
-        // ---- warp exclusive scan of T -----------------------------------------------------
-        uint32_t inc = T;
+        // padding samples of a short last slot were coded as delta 0: K+1 bits each
+        if (!kFull && nvalid < (uint32_t)S) T = nvalid ? T - ((uint32_t)S - nvalid) * (K + 1) : 0u;
+    } else {
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += t;
+        for (int j = 0; j < S; ++j) {
+            const uint32_t u = (j & 1) ? (U[j >> 1] >> 16) : (U[j >> 1] & 0xFFFFu);
+            rice_code<K>(u, iv[j], il[j]);
+            if (!kFull && (uint32_t)j >= nvalid) { iv[j] = 0; il[j] = 0; }
+            T += il[j];
         }
-        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-        const uint32_t b0 = base + inc - T;            // bit offset of this lane in the wave
+    }
 
-        // ---- pack ------------------------------------------------------------------------
-        Packer<kDirect> pk;
-        pk.n = b0 & 31u;
-        pk.ptr = dst + (b0 >> 5);
-        pk.end = dst + cap;
-        pk.lo = 0;
-        if (!kDirect && ((base + total + 31u) >> 5) + 16u > cap) ovf = true;   // warp uniform
-        const bool packs = nvalid > 0 && !ovf;
-        if (packs) {
-            if (kPairs) {
+    // ---- warp exclusive scan of T ----------------------------------------------------------
+    uint32_t inc = T;
 #pragma unroll
-                for (int m = 0; m < 8; m += 2) {
-                    if (flagged && ((il[m] | il[m + 1]) & 0x80u)) {
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    const uint32_t b0 = st.base + inc - T;           // bit offset of this lane in the wave
+    st.base += total;
+    if (!kDirect && ((st.base + 31u) >> 5) + 16u > cap) st.ovf = true;
+    if (st.ovf) return;                              // warp uniform: sizing only
+
+    // ---- pack ----------------------------------------------------------------------------------
+    Packer<kDirect> pk;
+    pk.n = b0 & 31u;
+    uint32_t *const first = dst + (b0 >> 5);
+    pk.ptr = first;
+    pk.end = dst + cap;
+    pk.lo = 0;
+    const bool packs = kFull || nvalid > 0;
+    if (packs) {
+        if (kPairs) {
+            if (!any_flag) {
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            if (il[m + e] & 0x80u) {
-                                uint32_t v0, l0, v1, l1;
-                                rice_code<K>(iv[m + e] & 0xFFFFu, v0, l0);
-                                rice_code<K>(iv[m + e] >> 16, v1, l1);
-                                pk.put(v0, l0);
-                                pk.put(v1, l1);
-                            } else {
-                                pk.put(iv[m + e], il[m + e]);
-                            }
-                        }
-                    } else {
-                        pk.put2(iv[m], il[m], iv[m + 1], il[m + 1]);
-                    }
-                }
+                for (int m = 0; m < 8; ++m) pk.put(iv[m], il[m]);
             } else {
 #pragma unroll
-                for (int j = 0; j < S; ++j)
-                    if (il[j]) pk.put(iv[j], il[j]);
+                for (int m = 0; m < 8; ++m) {
+                    if (il[m] & 0x80u) {
+                        uint32_t v0, l0, v1, l1;
+                        rice_code<K>(iv[m] & 0xFFFFu, v0, l0);
+                        rice_code<K>(iv[m] >> 16, v1, l1);
+                        pk.put(v0, l0);
+                        pk.put(v1, l1);
+                    } else {
+                        pk.put(iv[m], il[m]);
+                    }
+                }
             }
-        }
-        // ---- stitch the lanes: the bits a lane left pending belong to the first word the
-        // next lane wrote (or still holds) -------------------------------------------------
-        uint32_t frag;                                       // pending bits, left aligned
-        asm("shl.b32 %0, %1, %2;" : "=r"(frag) : "r"(pk.lo), "r"(32u - pk.n));   // n == 0 -> 0
-        if (nvalid == 0) frag = 0;
-        const bool flushed = pk.ptr != dst + (b0 >> 5);      // wrote its first word itself
-        constexpr int kStitch = (K == 0) ? 2 : 1;            // 1-bit codes: a lane may hold < 32 bits
+        } else {
 #pragma unroll
-        for (int e = 0; e < kStitch; ++e) {
-            uint32_t from_prev = __shfl_up_sync(0xffffffffu, frag, 1);
-            if (lane == 0) from_prev = carry_round;
-            if (packs) {
-                if (flushed) { if (from_prev) dst[b0 >> 5] |= from_prev; }
-                else frag |= from_prev;
-            }
+            for (int j = 0; j < S; ++j)
+                if (kFull || il[j]) pk.put(iv[j], il[j]);
         }
-        carry_round = __shfl_sync(0xffffffffu, frag, 31);
-        // the wave's last lane owns the final partial word; bits past the wave's end (padding
-        // codes of a short slot) are cleared so the word is zero padded (:237-241)
-        base += total;
-        if (r + 1 == wv.nrounds && packs && s0 + S >= wv.n) {
-            if (pk.n) pk.store(pk.ptr, frag);
-            if (base & 31u) dst[base >> 5] &= 0xFFFFFFFFu << (32u - (base & 31u));
-        }
-        cur = nxt;
     }
+    // ---- stitch the lanes: the bits a lane left pending belong to the first word the next
+    // lane wrote (or still holds) --------------------------------------------------------------
+    uint32_t frag;                                       // pending bits, left aligned
+    asm("shl.b32 %0, %1, %2;" : "=r"(frag) : "r"(pk.lo), "r"(32u - pk.n));   // n == 0 -> 0
+    if (!packs) frag = 0;
+    const bool flushed = pk.ptr != first;                // wrote its first word itself
+    constexpr int kStitch = (K == 0) ? 2 : 1;            // 1-bit codes: a lane may hold < 32 bits
+#pragma unroll
+    for (int e = 0; e < kStitch; ++e) {
+        uint32_t from_prev = __shfl_up_sync(0xffffffffu, frag, 1);
+        if (lane == 0) from_prev = st.carry_round;
+        if (packs) {
+            if (flushed) { if (from_prev) *first |= from_prev; }
+            else frag |= from_prev;
+        }
+    }
+    st.carry_round = __shfl_sync(0xffffffffu, frag, 31);
+    // the wave's last lane owns the final partial word; bits past the wave's end (padding codes
+    // of a short slot) are cleared so the word is zero padded (:237-241)
+    if (!kFull && last_lane && packs) {
+        if (pk.n) pk.store(pk.ptr, frag);
+        if (st.base & 31u) dst[st.base >> 5] &= 0xFFFFFFFFu << (32u - (st.base & 31u));
+    }
+}
+
+// Encoding sweep over one wave.  kDirect = false: packs into the warp's staging of `cap` words;
+// when the wave outgrows it, packing stops (sizing continues) and *overflow is set.
+// kDirect = true: packs straight into the record in HBM, `cap` = the wave's word count (nothing
+// is stored past it).  Returns the wave's bit count.
+template <int K, bool kDirect>
+__device__ __forceinline__ uint32_t encode_wave(const int16_t *wave, uint32_t n, const int16_t *raw_hi, int lane,
+                                                uint32_t *dst, uint32_t cap, bool *overflow)
+{
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(wave) & 15u) >> 1);
+    // rounds in which every lane holds 16 samples inside the buffer; then one generic round
+    uint32_t nfull = n / kRound;
+    const bool has_tail = (n % kRound) != 0;
+    if (!has_tail && nfull) {
+        // the wave's last lane must close the final word: run the last full round as the tail
+        --nfull;
+    }
+    SweepState st;
+    st.base = 0;
+    st.carry_round = 0;
+    st.prev_last = 0;
+    st.ovf = false;
+    // the next round's samples are always in flight while the current round is encoded
+    const uint32_t tail_s0 = nfull * kRound + lane * S;
+    const int32_t tail_rem = (int32_t)n - (int32_t)tail_s0;
+    const uint32_t tail_valid = tail_rem >= S ? (uint32_t)S : (tail_rem > 0 ? (uint32_t)tail_rem : 0u);
+    const int16_t *q = wave + lane * S;
+    RawWords cur;
+    if (nfull) load_slot(cur, q, mis); else load_slot_tail(cur, wave + tail_s0, mis, tail_valid, raw_hi);
+    for (uint32_t r = 0; r < nfull; ++r) {
+        RawWords now = cur;
+        q += kRound;
+        if (r + 1 < nfull) load_slot(cur, q, mis); else load_slot_tail(cur, wave + tail_s0, mis, tail_valid, raw_hi);
+        encode_round<K, kDirect, true>(now, S, false, lane, dst, cap, st);
+    }
+    encode_round<K, kDirect, false>(cur, tail_valid, tail_valid > 0 && tail_s0 + S >= n, lane, dst, cap, st);
     __syncwarp();
-    *overflow = ovf;
-    return base;
+    *overflow = st.ovf;
+    return st.base;
 }
 
 // ---- tile kernel ----------------------------------------------------------------------------
 // A tile = kEncWarps consecutive waves, taken by one persistent CTA of kEncWarps worker warps +
 // one control warp.  Per iteration a worker encodes ONE wave of the current tile into one of its
 // two staging buffers (single sweep over HBM), then copies out the wave it encoded in the
-// previous iteration, whose position has been resolved in the meantime by the control warp:
-// after the one barrier of the iteration the control warp sums the tile's wave sizes, publishes
-// the aggregate and resolves the tile's offset among all tiles by decoupled look-back, while the
-// workers are already encoding the next tile.  No worker waits on global memory latency, and
-// only one look-back per tile is in flight per CTA.
+// previous iteration, whose position has been resolved in the meantime:
+//   * the worker that finishes its wave last sums the tile's wave sizes and publishes the tile's
+//     aggregate at once (nobody ever waits for a size that is already known);
+//   * the control warp resolves tile after tile by decoupled look-back and hands the offsets to
+//     the workers through shared memory, one iteration behind them.
+// Shared control state lives in a ring of 3 slots (iteration % 3): a slot is reused only after
+// the workers have copied out the tile two iterations back, which needs the control warp to be
+// done with it.
+constexpr int kRing = 3;
+
 template <int K>
 __global__ void __launch_bounds__((kEncWarps + 1) * 32)
 encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint32_t ntiles)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ uint32_t s_tile[2];
-    __shared__ uint32_t s_mine[2][kEncWarps];
-    __shared__ uint64_t s_off[2];
-    __shared__ volatile uint32_t s_flag[2];
+    __shared__ uint32_t s_tile[kRing];                   // tile index of the iteration
+    __shared__ uint32_t s_mine[kRing][kEncWarps];        // words each wave contributes
+    __shared__ uint32_t s_cnt[kRing];                    // workers that have reported
+    __shared__ uint32_t s_total[kRing];
+    __shared__ volatile uint32_t s_ready[kRing];         // = it + 1 once s_total is valid
+    __shared__ uint64_t s_off[kRing];                    // tile's exclusive word offset
+    __shared__ volatile uint32_t s_flag[kRing];          // = it + 1 once s_off is valid
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool control = warp == kEncWarps;
 
-    if (threadIdx.x == 0) { s_flag[0] = 0; s_flag[1] = 0; }
-    if (control && lane == 0) s_tile[0] = atomicAdd(p.ticket, 1u);
+    if (threadIdx.x < kRing) { s_flag[threadIdx.x] = 0; s_ready[threadIdx.x] = 0; s_cnt[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) s_tile[0] = atomicAdd(p.ticket, 1u);
     __syncthreads();
 
     if (control) {
         for (uint32_t it = 0;; ++it) {
-            const int par = it & 1;
-            const uint32_t tile = s_tile[par];
+            const int slot = it % kRing;
+            while (s_ready[slot] != it + 1) __nanosleep(100);
+            __threadfence_block();
+            const uint32_t tile = s_tile[slot];
             if (tile >= ntiles) break;
-            if (lane == 0) s_tile[par ^ 1] = atomicAdd(p.ticket, 1u);
-            __syncthreads();                                 // B(it): wave sizes of the tile
-            const uint32_t v = lane < kEncWarps ? s_mine[par][lane] : 0u;
-            const uint64_t mine = __reduce_add_sync(0xffffffffu, v);
-            if (lane == 0) st_relaxed_u64(p.lookback + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | mine);
+            const uint64_t mine = s_total[slot];
             const uint64_t excl = lookback_excl(p.lookback, tile, mine, lane);
             if (lane == 0) {
-                s_off[par] = excl;
+                s_off[slot] = excl;
                 __threadfence_block();
-                s_flag[par] = it + 1;
+                s_flag[slot] = it + 1;
                 if (excl + mine > p.out_cap_words) atomicOr(p.status, kErrCapacity);
                 if (tile == ntiles - 1) p.chunk_byte_off[p.nchunks] = (excl + mine) * 4;
             }
@@ -524,14 +543,17 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
 
     // ---- workers ---------------------------------------------------------------------------
     uint32_t *const stage0 = smem + (size_t)(2 * warp) * stage_words;   // two staging buffers per warp
+    const int16_t *const raw_hi = p.raw + p.raw_samples;
     WaveGeom wg_prev;
     uint32_t nwords_prev = 0;
     bool have_prev = false, ovf_prev = false;
     wg_prev.g = 0xffffffffu;
     for (uint32_t it = 0;; ++it) {
-        const int par = it & 1;
-        const uint32_t tile = s_tile[par];
+        const int par = it & 1, slot = it % kRing;
+        const uint32_t tile = s_tile[slot];
         const bool live = tile < ntiles;
+        uint32_t next_ticket = 0;
+        if (live && threadIdx.x == 0) next_ticket = atomicAdd(p.ticket, 1u);   // consumed after the wave
         WaveGeom wg;
         uint32_t nwords = 0;
         bool have = false, ovf = false;
@@ -542,22 +564,41 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
                 have = true;
                 wg = locate_wave(p, g);
                 if (wg.chunk_total) {
-                    const WaveView wv(p, wg);
-                    nwords = (encode_wave<K, false>(wv, lane, stage0 + par * stage_words, stage_words, &ovf) + 31u) >> 5;
+                    nwords = (encode_wave<K, false>(p.raw + wg.begin, wg.n, raw_hi, lane, stage0 + par * stage_words,
+                                                    stage_words, &ovf) + 31u) >> 5;
                     mine = nwords + 1u;
                 }
                 mine += wg.first;                            // empty chunk: header only
             }
-            if (lane == 0) s_mine[par][warp] = mine;
+            if (lane == 0) {
+                s_mine[slot][warp] = mine;
+                __threadfence_block();
+                if (atomicAdd(&s_cnt[slot], 1u) == kEncWarps - 1) {
+                    // last worker of the tile: publish the tile's aggregate now
+                    __threadfence_block();
+                    uint32_t total = 0;
+#pragma unroll
+                    for (int w = 0; w < kEncWarps; ++w) total += s_mine[slot][w];
+                    st_relaxed_u64(p.lookback + tile, kFlagAggregate | (uint64_t)total);
+                    s_total[slot] = total;
+                    s_cnt[slot] = 0;
+                    __threadfence_block();
+                    s_ready[slot] = it + 1;
+                }
+            }
+        } else if (threadIdx.x == 0) {
+            __threadfence_block();
+            s_ready[slot] = it + 1;                          // lets the control warp see the end
         }
+        if (threadIdx.x == 0 && live) s_tile[(it + 1) % kRing] = next_ticket;
         // ---- copy out the wave of the previous iteration ------------------------------------
         if (have_prev) {
-            const int pp = par ^ 1;
-            const uint32_t v = lane < kEncWarps ? s_mine[pp][lane] : 0u;
-            const uint32_t loff = __reduce_add_sync(0xffffffffu, lane < warp ? v : 0u);
-            while (s_flag[pp] != it) __nanosleep(40);        // tile offset: normally there long ago
+            const int ps = (it + kRing - 1) % kRing;
+            while (s_flag[ps] != it) __nanosleep(40);        // tile offset: normally there long ago
             __threadfence_block();
-            const uint64_t off = s_off[pp] + loff;
+            const uint32_t v = lane < kEncWarps ? s_mine[ps][lane] : 0u;
+            const uint32_t loff = __reduce_add_sync(0xffffffffu, lane < warp ? v : 0u);
+            const uint64_t off = s_off[ps] + loff;
             const uint32_t rec_words = wg_prev.chunk_total ? nwords_prev + 1u : 0u;
             const bool fits = off + rec_words + wg_prev.first <= p.out_cap_words;
             if (lane == 0 && wg_prev.first) p.chunk_byte_off[wg_prev.chunk] = off * 4;
@@ -569,12 +610,11 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
                 }
                 if (rec_words) {
                     if (!ovf_prev) {
-                        const uint32_t *src = stage0 + pp * stage_words;
+                        const uint32_t *src = stage0 + (par ^ 1) * stage_words;
                         for (uint32_t i = lane; i < nwords_prev; i += 32) rec[1 + i] = src[i];
                     } else {                                 // larger than the staging: pack in place
-                        const WaveView wv(p, wg_prev);
                         bool dummy;
-                        encode_wave<K, true>(wv, lane, rec + 1, nwords_prev, &dummy);
+                        encode_wave<K, true>(p.raw + wg_prev.begin, wg_prev.n, raw_hi, lane, rec + 1, nwords_prev, &dummy);
                     }
                 }
             }
@@ -585,7 +625,8 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
         nwords_prev = nwords;
         have_prev = have;
         ovf_prev = ovf;
-        __syncthreads();                                     // B(it)
+        // workers only (the control warp runs on its own clock)
+        asm volatile("bar.sync 1, %0;" ::"n"(kEncWarps * 32) : "memory");
     }
 }
 
