@@ -523,7 +523,7 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
     if (control) {
         for (uint32_t it = 0;; ++it) {
             const int slot = it % kRing;
-            while (s_ready[slot] != it + 1) __nanosleep(100);
+            while (s_ready[slot] != it + 1) __nanosleep(400);
             __threadfence_block();
             const uint32_t tile = s_tile[slot];
             if (tile >= ntiles) break;
@@ -553,7 +553,6 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
         const uint32_t tile = s_tile[slot];
         const bool live = tile < ntiles;
         uint32_t next_ticket = 0;
-        if (live && threadIdx.x == 0) next_ticket = atomicAdd(p.ticket, 1u);   // consumed after the wave
         WaveGeom wg;
         uint32_t nwords = 0;
         bool have = false, ovf = false;
@@ -570,6 +569,9 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
                 }
                 mine += wg.first;                            // empty chunk: header only
             }
+            // next tile: taken as late as possible so that tiles start in ticket order; the
+            // atomic's latency hides behind the copy-out below
+            if (threadIdx.x == 0) next_ticket = atomicAdd(p.ticket, 1u);
             if (lane == 0) {
                 s_mine[slot][warp] = mine;
                 __threadfence_block();
@@ -590,7 +592,6 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
             __threadfence_block();
             s_ready[slot] = it + 1;                          // lets the control warp see the end
         }
-        if (threadIdx.x == 0 && live) s_tile[(it + 1) % kRing] = next_ticket;
         // ---- copy out the wave of the previous iteration ------------------------------------
         if (have_prev) {
             const int ps = (it + kRing - 1) % kRing;
@@ -621,6 +622,7 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
             __syncwarp();
         }
         if (!live) break;
+        if (threadIdx.x == 0) s_tile[(it + 1) % kRing] = next_ticket;
         wg_prev = wg;
         nwords_prev = nwords;
         have_prev = have;
