@@ -521,10 +521,11 @@ extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_co
     rc = upload_tables(ctx, off, woff.data(), g.wave_off.data(), nchunks, st, &d_soff, &d_woff64, &d_wave_off);
     if (rc) return rc;
     const size_t nw = g.nwaves;
-    const size_t scratch = nw * (8 + 8 + 4) + 64;
+    const size_t scratch = nw * (8 + 8 + 4) + 64 + 16;
     if (scratch > ctx->d_scratch.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
     DR_CUDA(ctx, ctx->d_scratch.reserve(scratch));
-    uint64_t *wave_in = (uint64_t *)ctx->d_scratch.p;
+    DR_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch.p, 0, 16, st));      // parse ticket
+    uint64_t *wave_in = (uint64_t *)((char *)ctx->d_scratch.p + 16);
     uint64_t *wave_out = wave_in + nw;
     uint32_t *wave_n = (uint32_t *)(wave_out + nw);
 
@@ -553,14 +554,18 @@ extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_co
     pp.wave_n = wave_n;
     pp.out = d_out;
     pp.status = d_status;
+    pp.ticket = (uint32_t *)ctx->d_scratch.p;
     pp.nwaves = g.nwaves;
     pp.max_n = g.max_wave;
     pp.k = k;
-    const bool wide = g.wave_offsets_mult4 && (reinterpret_cast<uintptr_t>(d_out) & 7) == 0;
+    // widest store that every wave start allows
+    int store_bytes = (int)(g.align_samples * 2);
+    while (store_bytes > 2 && (reinterpret_cast<uintptr_t>(d_out) & (uintptr_t)(store_bytes - 1))) store_bytes >>= 1;
+    if (store_bytes == 4) store_bytes = 2;
     int nl;
     {
         TimedScope ts(ctx, DRICE_KERNEL_PARSE, st);
-        nl = launch_parse(pp, wide ? 8 : 2, st);
+        nl = launch_parse(pp, store_bytes, st);
     }
     if (nl < 0) return fail(ctx, DRICE_E_PARAM, "unsupported RiceParameter");
     ctx->launches += (uint64_t)nl;

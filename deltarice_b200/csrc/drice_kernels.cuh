@@ -66,6 +66,7 @@ struct ParseParams {
     const uint32_t *wave_n;
     int16_t        *out;
     uint32_t       *status;
+    uint32_t       *ticket;             // zeroed: warp tasks (32 waves each) handed out
     uint32_t        nwaves;
     uint32_t        max_n;              // longest wave in the batch
     int             k;
