@@ -379,7 +379,7 @@ extern "C" int drice_timing_read(drice_ctx *ctx, double *ms, uint64_t *launches,
 
 extern "C" const char *drice_kernel_name(int kind)
 {
-    static const char *names[DRICE_NUM_KERNELS] = {"encode_kernel", "locate_kernel", "parse_kernel"};
+    static const char *names[DRICE_NUM_KERNELS] = {"encode_tile_kernel", "locate_kernel", "parse_kernel"};
     return (kind >= 0 && kind < DRICE_NUM_KERNELS) ? names[kind] : nullptr;
 }
 

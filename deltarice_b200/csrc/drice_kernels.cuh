@@ -69,6 +69,7 @@ struct ParseParams {
     uint32_t       *ticket;             // zeroed: warp tasks (32 waves each) handed out
     uint32_t        nwaves;
     uint32_t        max_n;              // longest wave in the batch
+    uint32_t        smem_bytes;         // dynamic shared memory of the launch (set by the launcher)
     int             k;
 };
 
