@@ -22,6 +22,7 @@
 //                  that the warp then stores to HBM row by row, coalesced.
 #include "drice_kernels.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 
 namespace drice {
@@ -150,91 +151,232 @@ __global__ void __launch_bounds__(kLocThreads) locate_kernel(const LocateParams 
 // ------------------------------------------------------------------------------------
 // Rice parsing is a serial chain per wave (a code's length is only known once its unary
 // prefix has been read), so the parallelism is across waves: one LANE per wave, a warp takes
-// 32 consecutive waves per ticket.  What makes a lane fast is how many instructions it spends
-// per sample:
-//   * multi-symbol table: the next 12 stream bits index a shared-memory table built for the
-//     launch's k (4096 x 8 bytes) whose entry holds up to THREE complete codes already turned
-//     into running delta sums, the bits they consume and their count, so one lookup + two
-//     packed adds yields up to three samples.  Entries with no complete code (escape, or a code
-//     longer than 12 bits) send the lane through a count-leading-zeros path for one sample;
-//   * the compressed words reach the lane through a private 32-word ring in shared memory
-//     filled by 16-byte cp.async (no registers, latency hidden one refill period ahead);
-//   * samples are written to a per-warp shared tile (32 lanes x 32 samples) that the warp then
-//     stores to HBM row by row with 16-byte (or 8 / 2 byte, by alignment) coalesced stores.
+// 32 consecutive waves per ticket.  The kernel is bound by issue slots and by the shared-memory
+// (MIO) pipe, so the inner loop is built to touch shared memory as little as possible:
+//   * one code = one lookup: the next 12 stream bits index a shared-memory table built for the
+//     launch's k whose 4-byte entry is (delta << 16 | bits consumed); escapes and codes longer
+//     than the window miss (entry 0) and take a count-leading-zeros path;
+//   * a step decodes exactly TWO samples (two chained lookups in a 96-bit register window), so
+//     every lane of the warp advances in lock step and the two 16-bit results pack into one
+//     register; four steps fill a 16-byte block that the lane stores straight to HBM - there is
+//     no shared-memory staging of the output at all;
+//   * the compressed words reach the lane through a private 16-word ring in shared memory
+//     ([word][lane], bank = lane: conflict free), refilled with one 16-byte load per block that is
+//     requested a block ahead (plus an L2 prefetch two lines ahead).
 constexpr int kLutBits     = 12;
 constexpr int kLutSize     = 1 << kLutBits;
-constexpr int kTS          = 32;                 // samples per lane per output tile
-constexpr int kRowW        = 18;                 // words per tile row: 32 samples + 3 overshoot, 8-byte aligned
-constexpr int kRingWords   = 32;                 // ring words per lane (8 chunks of 16 bytes)
-constexpr int kWarpSmemW   = kRingWords * 32 + 32 * kRowW + 32 * 2 + 32;   // ring | tile | row base (u64) | row n
-constexpr int kRefillEvery = 16;                 // lookups between ring refills (<= 12.5 words consumed)
+constexpr int kRingWords   = 32;                 // compressed words per lane (4 KB per warp)
+constexpr int kParseMaxWarps = 17;               // per CTA; two CTAs per SM
 
-__device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, uint32_t src_bytes)
-{
-    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
-
-// table entry for the 12 bits `idx` (MSB = next stream bit), Rice parameter 2^k:
-//   x = S1 | S2 << 16,  y = S3 | nbits << 16 | 2*count << 24
-// S_i = sum of the first i decoded deltas (src/deltaRice.c:161-177), the unused ones repeat the
-// last, so S3 is always the total.  count = 0: no complete non-escape code in the window.
-__device__ __forceinline__ uint2 make_lut_entry(uint32_t idx, int k)
+// shared memory through 32-bit shared-window addresses (no generic address arithmetic in the loop)
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
 {
-    const uint32_t bits = idx << (32 - kLutBits);
-    uint32_t pos = 0, cnt = 0;
-    int sum = 0;
-    int S[3] = {0, 0, 0};
-    while (cnt < 3) {
-        const uint32_t rem = kLutBits - pos;
-        const uint32_t win = bits << pos;
-        const uint32_t q = win ? (uint32_t)__clz(win) : 32u;
-        if (q >= rem || q >= kEscapeQuotient) break;
-        const uint32_t len = q + 1 + (uint32_t)k;
-        if (len > rem) break;
-        const uint32_t r = (win >> (32 - len)) & ((1u << k) - 1u);
-        const uint32_t u = (q << k) | r;
-        sum += (u & 1u) ? -(int)((u + 1) >> 1) : (int)(u >> 1);
-        S[cnt++] = sum;
-        pos += len;
-    }
-    for (uint32_t i = cnt; i < 3 && cnt; ++i) S[i] = S[cnt - 1];
-    uint2 e;
-    e.x = ((uint32_t)S[0] & 0xFFFFu) | ((uint32_t)S[1] << 16);
-    e.y = ((uint32_t)S[2] & 0xFFFFu) | (pos << 16) | ((2u * cnt) << 24);
-    return e;
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ldg_cg_u4(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"      // L2 only: every lane streams its own record
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+// one full 32-byte sector per lane: partial-sector stores make L2 read the sector from DRAM first
+__device__ __forceinline__ void stg_256(void *p, const uint4 &a, const uint4 &b)
+{
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-template <int STORE_BYTES>
-__global__ void __launch_bounds__(1024, 1) parse_kernel(const ParseParams p)
+// table entry for the kLutBits bits `idx` (MSB = next stream bit), Rice parameter 2^k:
+// (delta << 16) | bits consumed for the one complete non-escape code the window starts with
+// (src/deltaRice.c:161-177), 0 if there is none.
+__device__ __forceinline__ uint32_t make_lut_entry(uint32_t idx, int k)
+{
+    const uint32_t win = idx << (32 - kLutBits);
+    const uint32_t q = win ? (uint32_t)__clz(win) : 32u;
+    const uint32_t len = q + 1 + (uint32_t)k;
+    if (q >= kEscapeQuotient || len > (uint32_t)kLutBits) return 0u;
+    const uint32_t r = (win >> (32 - len)) & ((1u << k) - 1u);
+    const uint32_t u = (q << k) | r;
+    const int d = (u & 1u) ? -(int)((u + 1) >> 1) : (int)(u >> 1);
+    return ((uint32_t)d << 16) | len;
+}
+
+// where a lane's compressed words come from (one wave)
+struct RingFeed {
+    const uint32_t *gbase;      // 16-byte aligned address of chunk 0
+    const uint32_t *comp_al;    // aligned address at or below the stream
+    uint64_t base_al, lim_al;   // chunk 0 / end of the stream, words from comp_al
+    uint32_t mis;               // words between comp_al and the stream
+    uint32_t safe;              // chunks [0, safe) need no bounds checks
+    uint32_t ring_b;            // shared address of the lane's ring word 0 (region aligned to its size)
+    uint32_t fetched;           // words in the ring so far (multiple of 4), from chunk 0
+
+    __device__ __forceinline__ uint4 load_chunk(uint32_t at) const
+    {
+        if (at + 4 <= safe) return ldg_cg_u4(gbase + at);
+        const uint64_t aw = base_al + at;
+        uint32_t e[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e[i] = (aw + i >= mis && aw + i < lim_al) ? comp_al[aw + i] : 0u;
+        return make_uint4(e[0], e[1], e[2], e[3]);
+    }
+    __device__ __forceinline__ void store_chunk(uint32_t at, const uint4 &c) const
+    {
+        const uint32_t ad = ((at << 7) & ((kRingWords << 7) - 128u)) | ring_b;
+        sts32(ad, c.x); sts32(ad + 128, c.y); sts32(ad + 256, c.z); sts32(ad + 384, c.w);
+    }
+    __device__ __forceinline__ uint32_t word(uint32_t x) const
+    {
+        return lds32(((x << 7) & ((kRingWords << 7) - 128u)) | ring_b);
+    }
+    // synchronous top-up until `need` words (from chunk 0) are in the ring
+    __device__ __forceinline__ void ensure(uint32_t need)
+    {
+        while (fetched < need) {
+            store_chunk(fetched, load_chunk(fetched));
+            fetched += 4;
+        }
+    }
+};
+
+// decoder state of one lane: a 96-bit window w0:w1:w2 over the stream
+struct LaneDec {
+    uint32_t w0, w1, w2;
+    uint32_t bit;           // bits of w0 already consumed (< 32 between steps)
+    uint32_t wpos;          // position of w0 (words from the wave's chunk 0)
+    uint32_t acc;           // running sample (low 16 bits count)
+    bool     bad;
+
+    __device__ __forceinline__ void advance(RingFeed &rf)
+    {
+        if (bit >= 32u) {
+            bit -= 32u;
+            ++wpos;
+            w0 = w1;
+            w1 = w2;
+            w2 = rf.word(wpos + 2);
+        }
+    }
+    // one code that the table does not hold, through count-leading-zeros (src/deltaRice.c:154-177);
+    // `win` = the 32 stream bits at the current position.  Returns the delta.
+    __device__ __forceinline__ uint32_t slow_code(uint32_t win, RingFeed &rf, int k, uint32_t kmask, uint32_t &len)
+    {
+        const uint32_t q = __clz(win);
+        uint32_t u;
+        if (q >= kEscapeQuotient) {
+            bad |= (q > kEscapeQuotient);
+            u = (win >> 7) & 0xFFFFu;
+            len = kEscapeBits;
+        } else {
+            len = q + 1 + (uint32_t)k;
+            u = (q << k) | ((win >> (32u - len)) & kmask);
+        }
+        // the periodic refill only covers a block of table-path codes (<= 12 bits each): after an
+        // escape make sure the rest of the block (<= 6 more words + the window) is in the ring
+        rf.ensure(wpos + 12u);
+        const uint32_t h = u >> 1;
+        return (u & 1u) ? ~h : h;
+    }
+    // decodes ONE sample (prologue / epilogue of a wave); bit < 32 on entry and on exit
+    __device__ __forceinline__ uint32_t one(RingFeed &rf, uint32_t lut_s, int k, uint32_t kmask, uint32_t lutmask)
+    {
+        const uint32_t win = __funnelshift_l(w1, w0, bit);
+        const uint32_t e = lds32(lut_s + ((win >> (32 - kLutBits - 2)) & lutmask));
+        uint32_t dl, len;
+        if (e) {
+            dl = (uint32_t)((int32_t)e >> 16);
+            len = e & 31u;
+        } else {
+            dl = slow_code(win, rf, k, kmask, len);
+        }
+        acc += dl;
+        bit += len;
+        advance(rf);
+        return acc & 0xFFFFu;
+    }
+    // decodes TWO samples, packed lo | hi << 16; bit < 32 on entry and on exit
+    __device__ __forceinline__ uint32_t two(RingFeed &rf, uint32_t lut_s, int k, uint32_t kmask, uint32_t lutmask)
+    {
+        const uint32_t win1 = __funnelshift_l(w1, w0, bit);
+        const uint32_t e1 = lds32(lut_s + ((win1 >> (32 - kLutBits - 2)) & lutmask));
+        uint32_t d1, len1;
+        if (e1) {
+            d1 = (uint32_t)((int32_t)e1 >> 16);
+            len1 = e1 & 31u;
+        } else {
+            d1 = slow_code(win1, rf, k, kmask, len1);
+            bit += len1;
+            advance(rf);                 // an escape may cross a word: keep the second window in reach
+            len1 = 0;
+        }
+        const uint32_t b1 = bit + len1;                     // < 44
+        const bool hiw = b1 >= 32u;
+        const uint32_t win2 = __funnelshift_l(hiw ? w2 : w1, hiw ? w1 : w0, b1);
+        const uint32_t e2 = lds32(lut_s + ((win2 >> (32 - kLutBits - 2)) & lutmask));
+        const uint32_t y1 = acc + d1;
+        uint32_t d2, len2;
+        if (e2) {
+            d2 = (uint32_t)((int32_t)e2 >> 16);
+            len2 = e2 & 31u;
+        } else {
+            bit = b1;
+            advance(rf);
+            d2 = slow_code(__funnelshift_l(w1, w0, bit), rf, k, kmask, len2);
+            bit += len2;
+            advance(rf);
+            acc = y1 + d2;
+            return prmt(y1, acc, 0x5410);
+        }
+        acc = y1 + d2;
+        bit = b1 + len2;                                    // < 56
+        advance(rf);
+        return prmt(y1, acc, 0x5410);
+    }
+};
+
+__global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const ParseParams p)
 {
     extern __shared__ __align__(16) uint32_t dsm[];
-    uint2 *lut = reinterpret_cast<uint2 *>(dsm);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *wsm = dsm + 2 * kLutSize + (size_t)warp * kWarpSmemW;
-    uint32_t *ring = wsm;                                   // [chunk 0..7][lane][4 words]
-    uint32_t *tile = ring + kRingWords * 32;                // [row = lane][kRowW]
-    uint64_t *s_rowbase = reinterpret_cast<uint64_t *>(tile + 32 * kRowW);
-    uint32_t *s_rown = reinterpret_cast<uint32_t *>(s_rowbase + 32);
+    // shared layout: [pad to 2 KB] one 2 KB ring per warp | table
+    const uint32_t dsm_s = (uint32_t)__cvta_generic_to_shared(dsm);
+    const uint32_t nwarps = blockDim.x >> 5;
+    const uint32_t rings_s = (dsm_s + kRingWords * 128u - 1u) & ~(kRingWords * 128u - 1u);
+    const uint32_t lut_s = rings_s + nwarps * (kRingWords * 128u);
+    if (lut_s + kLutSize * 4u > dsm_s + p.smem_bytes) {     // launcher and kernel disagree on the layout
+        if (threadIdx.x == 0) atomicOr(p.status, kErrStream);
+        return;
+    }
     const int k = p.k;
+    const uint32_t kmask = (1u << k) - 1u;
+    const bool dbg_nostore = (p.max_n >> 31) & 1u;
+    const uint32_t dbg_lutmask = ((p.max_n >> 30) & 1u) ? 0x7Cu : ((kLutSize - 1) << 2);
 
-    for (uint32_t i = threadIdx.x; i < (uint32_t)kLutSize; i += blockDim.x) lut[i] = make_lut_entry(i, k);
+    for (uint32_t i = threadIdx.x; i < (uint32_t)kLutSize; i += blockDim.x) sts32(lut_s + 4u * i, make_lut_entry(i, k));
     __syncthreads();
 
-    // the ring holds 16-byte chunks that are aligned in memory: positions are words relative to
-    // the aligned address at or below p.comp
+    // compressed words are fetched as 16-byte chunks that are aligned in memory: positions are
+    // words relative to the aligned address at or below p.comp
     const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(p.comp) >> 2) & 3u);
     const uint32_t *comp_al = p.comp - mis;
     const uint64_t lim_al = p.comp_words + mis;             // end of the stream, aligned-relative
-    uint32_t *ring_lane = ring + lane * 4;
-    unsigned char *row_bytes = reinterpret_cast<unsigned char *>(tile + lane * kRowW);
     const uint32_t ngroups = (p.nwaves + 31u) / 32u;
 
     while (true) {
@@ -247,168 +389,98 @@ __global__ void __launch_bounds__(1024, 1) parse_kernel(const ParseParams p)
         const uint32_t n = active ? __ldg(p.wave_n + g) : 0u;
         const uint64_t rec = active ? __ldg(p.wave_in + g) : 0ull;        // word index of [nwords]
         const uint64_t obase = active ? __ldg(p.wave_out + g) : 0ull;     // sample offset of the wave
-        const uint32_t nmax = __reduce_max_sync(0xffffffffu, n);
-        if (nmax == 0) continue;
         const uint32_t nwords = n ? __ldg(p.comp + rec) : 0u;
+        int16_t *optr = p.out + obase;
 
-        // ---- ring: chunk `c` of this lane sits at ring_lane + (c & 7) * 128 words -----------
-        const uint64_t base_al = (rec + 1 + mis) & ~3ull;   // aligned-relative index of the chunk holding the first code word
-        uint32_t wpos = (uint32_t)((rec + 1 + mis) - base_al);   // position of w0, words from base_al
-        uint32_t fetched = 0;                               // words requested so far (multiple of 4), from base_al
-        auto issue_chunk = [&](uint32_t at) {
-            uint32_t *dst = ring_lane + ((at >> 2) & 7u) * 128u;
-            const uint64_t aw = base_al + at;               // aligned-relative word index of the chunk
-            if (aw >= mis && aw + 4 <= lim_al) {
-                cp_async16_zfill(dst, comp_al + aw, 16u);
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) dst[e] = (aw + e >= mis && aw + e < lim_al) ? comp_al[aw + e] : 0u;
-            }
-        };
-        auto ring_word = [&](uint32_t x) -> uint32_t {
-            return ring_lane[((x & 28u) << 5) + (x & 3u)];
-        };
+        RingFeed rf;
+        rf.base_al = (rec + 1 + mis) & ~3ull;               // aligned-relative index of the chunk holding the first code word
+        rf.gbase = comp_al + rf.base_al;
+        rf.comp_al = comp_al;
+        rf.lim_al = lim_al;
+        rf.mis = mis;
+        rf.safe = (rf.base_al >= mis)
+            ? (uint32_t)(lim_al - rf.base_al > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : ((lim_al - rf.base_al) & ~3ull)) : 0u;
+        rf.ring_b = rings_s + warp * (kRingWords * 128u) + lane * 4u;
+        rf.fetched = 0;
+
+        LaneDec d;
+        d.wpos = (uint32_t)((rec + 1 + mis) - rf.base_al);
+        d.bit = 0; d.acc = 0; d.bad = false; d.w0 = d.w1 = d.w2 = 0;
         __syncwarp();
         if (n) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) issue_chunk(4u * c);
-            fetched = 32;
+            for (int c = 0; c < kRingWords / 4; c += 2) {
+                const uint4 c0 = rf.load_chunk(4u * c), c1 = rf.load_chunk(4u * c + 4);
+                rf.store_chunk(4u * c, c0);
+                rf.store_chunk(4u * c + 4, c1);
+            }
+            rf.fetched = kRingWords;
+            d.w0 = rf.word(d.wpos);
+            d.w1 = rf.word(d.wpos + 1);
+            d.w2 = rf.word(d.wpos + 2);
         }
-        s_rowbase[lane] = obase;
-        s_rown[lane] = n;
-        cp_async_wait_all();
-        __syncwarp();
-        uint32_t w0 = ring_word(wpos), w1 = ring_word(wpos + 1);
-        uint32_t bit = 0;
-        uint32_t acc2 = 0;                                  // running sample in both halves
-        uint32_t jb = 0;                                    // bytes of samples in the current tile row
-        bool bad = false;
 
-        for (uint32_t t0 = 0; t0 < nmax; t0 += kTS) {
-            const int32_t left = (int32_t)n - (int32_t)t0;  // samples of this lane's wave from t0 on
-            const uint32_t limit_b = left >= kTS ? 2u * kTS : (left > 0 ? 2u * (uint32_t)left : 0u);
-            const bool exact = left <= kTS + 2;             // end of the wave: one code at a time, exact end position
-            uint32_t it = 0;
-            while (jb < limit_b) {
-                if ((it++ & (kRefillEvery - 1)) == 0) {
-                    // everything requested earlier has landed; top the ring up (the chunk holding
-                    // w0 must stay)
-                    cp_async_wait_all();
-                    const uint32_t room_end = (wpos & ~3u) + kRingWords;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        if (fetched + 4 <= room_end) {
-                            issue_chunk(fetched);
-                            fetched += 4;
-                        }
+        // ---- prologue: single samples up to the first 32-byte boundary of the output --------------
+        uint32_t left = n;
+        {
+            const uint32_t a = (uint32_t)((reinterpret_cast<uintptr_t>(optr) >> 1) & 15u);
+            uint32_t pro = (16u - a) & 15u;
+            if (pro > left) pro = left;
+            left -= pro;
+            if (pro) rf.ensure(d.wpos + 10u);
+            for (; pro; --pro) *optr++ = (int16_t)d.one(rf, lut_s, k, kmask, dbg_lutmask);
+        }
+        // ---- blocks of 16 samples: 8 steps of two, one 32-byte store (a full sector) -------------------
+        uint32_t nblk = left >> 4;
+        left &= 15u;
+        const uint32_t maxblk = __reduce_max_sync(0xffffffffu, nblk);
+        for (uint32_t b = 0; b < maxblk; ++b) {
+            if (b < nblk) {
+                // ring refill: the chunks requested now go in after the block's steps (a block uses at
+                // most 6 words through the table; longer codes top up on demand)
+                rf.ensure(d.wpos + 10u);
+                uint4 pend0 = make_uint4(0, 0, 0, 0), pend1 = pend0;
+                uint32_t pend_at = 0xffffffffu, npend = 0;
+                const uint32_t room = (d.wpos & ~3u) + kRingWords - rf.fetched;
+                if (room >= 4) {
+                    pend_at = rf.fetched;
+                    pend0 = rf.load_chunk(rf.fetched);
+                    npend = 1;
+                    if (room >= 8) {
+                        pend1 = rf.load_chunk(rf.fetched + 4);
+                        npend = 2;
                     }
+                    // the line two ahead: the request of a later block then hits L2
+                    if (rf.fetched + 68 <= rf.safe) prefetch_l2(rf.gbase + rf.fetched + 64);
                 }
-                const uint32_t win = __funnelshift_l(w1, w0, bit);
-                const uint2 e = lut[win >> (32 - kLutBits)];
-                const uint32_t cnt2 = e.y >> 24;
-                if (cnt2 != 0 && !exact) {
-                    const uint32_t y12 = __vadd2(e.x, acc2);
-                    const uint32_t y3 = __vadd2(e.y, acc2);
-                    unsigned char *q = row_bytes + jb;
-                    *reinterpret_cast<uint16_t *>(q) = (uint16_t)y12;
-                    *reinterpret_cast<uint16_t *>(q + 2) = (uint16_t)(y12 >> 16);
-                    *reinterpret_cast<uint16_t *>(q + 4) = (uint16_t)y3;
-                    acc2 = prmt(y3, 0, 0x1010);
-                    jb += cnt2;
-                    bit += prmt(e.y, 0, 0x4442);
-                } else {
-                    // one code through count-leading-zeros (src/deltaRice.c:154-177)
-                    const uint32_t q = __clz(win);
-                    uint32_t u, len;
-                    if (q >= kEscapeQuotient) {
-                        bad |= (q > kEscapeQuotient);
-                        u = (win >> 7) & 0xFFFFu;
-                        len = kEscapeBits;
-                    } else {
-                        len = q + 1 + (uint32_t)k;
-                        u = (q << k) | ((win >> (32u - len)) & ((1u << k) - 1u));
-                    }
-                    const uint32_t h = u >> 1;
-                    const uint32_t y = (acc2 + ((u & 1u) ? ~h : h)) & 0xFFFFu;
-                    *reinterpret_cast<uint16_t *>(row_bytes + jb) = (uint16_t)y;
-                    acc2 = y | (y << 16);
-                    jb += 2;
-                    bit += len;
+                uint4 o0, o1;
+                o0.x = d.two(rf, lut_s, k, kmask, dbg_lutmask);
+                o0.y = d.two(rf, lut_s, k, kmask, dbg_lutmask);
+                o0.z = d.two(rf, lut_s, k, kmask, dbg_lutmask);
+                o0.w = d.two(rf, lut_s, k, kmask, dbg_lutmask);
+                o1.x = d.two(rf, lut_s, k, kmask, dbg_lutmask);
+                o1.y = d.two(rf, lut_s, k, kmask, dbg_lutmask);
+                o1.z = d.two(rf, lut_s, k, kmask, dbg_lutmask);
+                o1.w = d.two(rf, lut_s, k, kmask, dbg_lutmask);
+                if (!dbg_nostore) stg_256(optr, o0, o1);
+                optr += 16;
+                if (pend_at == rf.fetched) {                 // (an on-demand top-up may have overtaken it)
+                    rf.store_chunk(rf.fetched, pend0);
+                    if (npend == 2) rf.store_chunk(rf.fetched + 4, pend1);
+                    rf.fetched += 4 * npend;
                 }
-                if (bit >= 32u) {
-                    bit -= 32u;
-                    ++wpos;
-                    w0 = w1;
-                    w1 = ring_word(wpos + 1);
-                }
-            }
-            __syncwarp();
-            // ---- store the tile: row r = wave of lane r, samples [t0, t0 + 32) -----------------
-            if (STORE_BYTES == 16) {
-                const int sub = lane >> 2, col = (lane & 3) * 8;              // 4 lanes x 16 bytes per row
-#pragma unroll
-                for (int itr = 0; itr < 4; ++itr) {
-                    const int r = itr * 8 + sub;
-                    const uint32_t rn = s_rown[r];
-                    const uint32_t cntr = rn > t0 ? min(rn - t0, (uint32_t)kTS) : 0u;
-                    const uint2 a = *reinterpret_cast<const uint2 *>(tile + r * kRowW + (col >> 1));
-                    const uint2 b = *reinterpret_cast<const uint2 *>(tile + r * kRowW + (col >> 1) + 2);
-                    int16_t *dst = p.out + s_rowbase[r] + t0 + col;
-                    if ((uint32_t)col + 8 <= cntr) {
-                        *reinterpret_cast<uint4 *>(dst) = make_uint4(a.x, a.y, b.x, b.y);
-                    } else {
-                        const uint32_t ev[4] = {a.x, a.y, b.x, b.y};
-                        for (int s = 0; s < 8; ++s)
-                            if ((uint32_t)(col + s) < cntr) dst[s] = (int16_t)(ev[s >> 1] >> ((s & 1) * 16));
-                    }
-                }
-            } else if (STORE_BYTES == 8) {
-                const int sub = lane >> 3, col = (lane & 7) * 4;              // 8 lanes x 8 bytes per row
-#pragma unroll
-                for (int itr = 0; itr < 8; ++itr) {
-                    const int r = itr * 4 + sub;
-                    const uint32_t rn = s_rown[r];
-                    const uint32_t cntr = rn > t0 ? min(rn - t0, (uint32_t)kTS) : 0u;
-                    const uint2 a = *reinterpret_cast<const uint2 *>(tile + r * kRowW + (col >> 1));
-                    int16_t *dst = p.out + s_rowbase[r] + t0 + col;
-                    if ((uint32_t)col + 4 <= cntr) {
-                        *reinterpret_cast<uint2 *>(dst) = a;
-                    } else {
-                        const uint32_t ev[2] = {a.x, a.y};
-                        for (int s = 0; s < 4; ++s)
-                            if ((uint32_t)(col + s) < cntr) dst[s] = (int16_t)(ev[s >> 1] >> ((s & 1) * 16));
-                    }
-                }
-            } else {
-                // generic alignment: 2-byte stores, one row per instruction
-#pragma unroll 4
-                for (int r = 0; r < 32; ++r) {
-                    const uint32_t rn = s_rown[r];
-                    const uint32_t cntr = rn > t0 ? min(rn - t0, (uint32_t)kTS) : 0u;
-                    int16_t *dst = p.out + s_rowbase[r] + t0;
-                    if ((uint32_t)lane < cntr) {
-                        const uint32_t wv = tile[r * kRowW + (lane >> 1)];
-                        dst[lane] = (int16_t)(wv >> ((lane & 1) * 16));
-                    }
-                }
-            }
-            __syncwarp();
-            // samples decoded past the tile's end open the next tile
-            if (jb > 2u * kTS) {
-                const uint32_t over = jb - 2u * kTS;             // 2 or 4 bytes
-                const uint32_t c0 = *reinterpret_cast<const uint32_t *>(row_bytes + 2 * kTS);
-                *reinterpret_cast<uint32_t *>(row_bytes) = c0;
-                jb = over;
-            } else {
-                jb = 0;
             }
         }
+        // ---- epilogue: the last < 8 samples --------------------------------------------------------
+        if (left) rf.ensure(d.wpos + 10u);
+        for (; left; --left) *optr++ = (int16_t)d.one(rf, lut_s, k, kmask, dbg_lutmask);
+
         // the codes must end inside the last word of the record
         if (n) {
-            const uint64_t used = (base_al + wpos) - (rec + 1 + mis) + (bit ? 1u : 0u);
-            if (used != nwords) bad = true;
+            const uint64_t used = (rf.base_al + d.wpos) - (rec + 1 + mis) + (d.bit ? 1u : 0u);
+            if (used != nwords) d.bad = true;
         }
-        if (bad) atomicOr(p.status, kErrStream);
+        if (d.bad) atomicOr(p.status, kErrStream);
     }
 }
 
@@ -428,8 +500,7 @@ int pick_parse_warps(uint32_t ngroups, int sms, int max_warps)
     return best;
 }
 
-template <int STORE_BYTES>
-int launch_parse_t(const ParseParams &p, cudaStream_t st)
+int launch_parse_impl(const ParseParams &p, cudaStream_t st)
 {
     if (!g_dec_sms) {
         int dev = 0;
@@ -439,29 +510,41 @@ int launch_parse_t(const ParseParams &p, cudaStream_t st)
     }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(parse_kernel<STORE_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        cudaFuncSetAttribute(parse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         attr_set = true;
     }
     const uint32_t ngroups = (p.nwaves + 31u) / 32u;
     static int max_warps = 0;
     if (!max_warps) {
         const char *e = getenv("DRICE_DEC_WARPS");
-        max_warps = e ? atoi(e) : 24;
+        max_warps = e ? atoi(e) : kParseMaxWarps;
         if (max_warps < 1) max_warps = 1;
-        if (max_warps > 28) max_warps = 28;
+        if (max_warps > kParseMaxWarps) max_warps = kParseMaxWarps;
     }
-    int warps = pick_parse_warps(ngroups, g_dec_sms, max_warps);
-    uint32_t grid = (uint32_t)g_dec_sms;
+    // two CTAs per SM; warps per CTA trimmed so that the last round of warp tasks is nearly full
+    const int ctas = 2 * g_dec_sms;
+    int warps = pick_parse_warps(ngroups, ctas, max_warps);
+    uint32_t grid = (uint32_t)ctas;
     if ((uint64_t)grid * warps > ngroups) {
-        // small batch: spread the groups over the SMs
-        grid = (ngroups + warps - 1) / warps;
-        if (grid < (uint32_t)g_dec_sms && ngroups >= (uint32_t)g_dec_sms) grid = (uint32_t)g_dec_sms;
-        if (grid > (uint32_t)g_dec_sms) grid = (uint32_t)g_dec_sms;
+        // small batch: spread the groups over the CTAs
+        grid = ngroups < (uint32_t)ctas ? ngroups : (uint32_t)ctas;
         warps = (int)((ngroups + grid - 1) / grid);
         if (warps < 1) warps = 1;
     }
-    const size_t smem = (size_t)(2 * kLutSize + warps * kWarpSmemW) * sizeof(uint32_t);
-    parse_kernel<STORE_BYTES><<<grid, warps * 32, smem, st>>>(p);
+    // shared layout: [pad to 2 KB] rings | table.  The dynamic area starts right after the 1 KB the
+    // system reserves per CTA (the kernel checks the assumption).
+    size_t off = 1024;
+    off = (off + kRingWords * 128 - 1) & ~(size_t)(kRingWords * 128 - 1);
+    off += (size_t)warps * kRingWords * 128 + (size_t)kLutSize * 4;
+    ParseParams pp = p;
+    pp.smem_bytes = (uint32_t)(off - 1024);
+    if (getenv("DRICE_DEBUG")) {
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, parse_kernel, warps * 32, pp.smem_bytes);
+        fprintf(stderr, "parse: grid %u warps %d smem %u occ %d\n", grid, warps, pp.smem_bytes, occ);
+    }
+    parse_kernel<<<grid, warps * 32, pp.smem_bytes, st>>>(pp);
     return 1;
 }
 
@@ -482,11 +565,10 @@ int launch_locate(const LocateParams &p, cudaStream_t st)
 
 int launch_parse(const ParseParams &p, int store_bytes, cudaStream_t st)
 {
+    (void)store_bytes;          // every alignment takes the same path: 16-byte aligned blocks per lane
     if (p.nwaves == 0) return 0;
     if (p.k < 0 || p.k > 15) return -1;
-    if (store_bytes >= 16) return launch_parse_t<16>(p, st);
-    if (store_bytes >= 8) return launch_parse_t<8>(p, st);
-    return launch_parse_t<2>(p, st);
+    return launch_parse_impl(p, st);
 }
 
 }  // namespace drice
