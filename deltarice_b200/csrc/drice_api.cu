@@ -556,7 +556,7 @@ extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_co
     pp.status = d_status;
     pp.ticket = (uint32_t *)ctx->d_scratch.p;
     pp.nwaves = g.nwaves;
-    pp.max_n = g.max_wave | (getenv("DRICE_DBG") ? ((uint32_t)atoi(getenv("DRICE_DBG")) << 29) : 0u);
+    pp.max_n = g.max_wave;
     pp.k = k;
     // widest store that every wave start allows
     int store_bytes = (int)(g.align_samples * 2);

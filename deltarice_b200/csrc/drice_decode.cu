@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kLocThreads) locate_kernel(const LocateParams 
 //     no shared-memory staging of the output at all;
 //   * the compressed words reach the lane through a private 16-word ring in shared memory
 //     ([word][lane], bank = lane: conflict free), refilled with one 16-byte load per block that is
-//     requested a block ahead (plus an L2 prefetch two lines ahead).
+//     requested a block ahead.
 constexpr int kLutBits     = 12;
 constexpr int kLutSize     = 1 << kLutBits;
 constexpr int kRingWords   = 32;                 // compressed words per lane (4 KB per warp)
@@ -198,11 +198,6 @@ __device__ __forceinline__ void stg_256(void *p, const uint4 &a, const uint4 &b)
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
                  "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
 }
-__device__ __forceinline__ void prefetch_l2(const void *p)
-{
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
 // table entry for the kLutBits bits `idx` (MSB = next stream bit), Rice parameter 2^k:
 // (delta << 16) | bits consumed for the one complete non-escape code the window starts with
 // (src/deltaRice.c:161-177), 0 if there is none.
@@ -295,10 +290,10 @@ struct LaneDec {
         return (u & 1u) ? ~h : h;
     }
     // decodes ONE sample (prologue / epilogue of a wave); bit < 32 on entry and on exit
-    __device__ __forceinline__ uint32_t one(RingFeed &rf, uint32_t lut_s, int k, uint32_t kmask, uint32_t lutmask)
+    __device__ __forceinline__ uint32_t one(RingFeed &rf, uint32_t lut_s, int k, uint32_t kmask)
     {
         const uint32_t win = __funnelshift_l(w1, w0, bit);
-        const uint32_t e = lds32(lut_s + ((win >> (32 - kLutBits - 2)) & lutmask));
+        const uint32_t e = lds32(lut_s + ((win >> (32 - kLutBits - 2)) & ((kLutSize - 1) << 2)));
         uint32_t dl, len;
         if (e) {
             dl = (uint32_t)((int32_t)e >> 16);
@@ -312,10 +307,10 @@ struct LaneDec {
         return acc & 0xFFFFu;
     }
     // decodes TWO samples, packed lo | hi << 16; bit < 32 on entry and on exit
-    __device__ __forceinline__ uint32_t two(RingFeed &rf, uint32_t lut_s, int k, uint32_t kmask, uint32_t lutmask)
+    __device__ __forceinline__ uint32_t two(RingFeed &rf, uint32_t lut_s, int k, uint32_t kmask)
     {
         const uint32_t win1 = __funnelshift_l(w1, w0, bit);
-        const uint32_t e1 = lds32(lut_s + ((win1 >> (32 - kLutBits - 2)) & lutmask));
+        const uint32_t e1 = lds32(lut_s + ((win1 >> (32 - kLutBits - 2)) & ((kLutSize - 1) << 2)));
         uint32_t d1, len1;
         if (e1) {
             d1 = (uint32_t)((int32_t)e1 >> 16);
@@ -329,7 +324,7 @@ struct LaneDec {
         const uint32_t b1 = bit + len1;                     // < 44
         const bool hiw = b1 >= 32u;
         const uint32_t win2 = __funnelshift_l(hiw ? w2 : w1, hiw ? w1 : w0, b1);
-        const uint32_t e2 = lds32(lut_s + ((win2 >> (32 - kLutBits - 2)) & lutmask));
+        const uint32_t e2 = lds32(lut_s + ((win2 >> (32 - kLutBits - 2)) & ((kLutSize - 1) << 2)));
         const uint32_t y1 = acc + d1;
         uint32_t d2, len2;
         if (e2) {
@@ -366,8 +361,6 @@ __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const Par
     }
     const int k = p.k;
     const uint32_t kmask = (1u << k) - 1u;
-    const bool dbg_nostore = (p.max_n >> 31) & 1u;
-    const uint32_t dbg_lutmask = ((p.max_n >> 30) & 1u) ? 0x7Cu : ((kLutSize - 1) << 2);
 
     for (uint32_t i = threadIdx.x; i < (uint32_t)kLutSize; i += blockDim.x) sts32(lut_s + 4u * i, make_lut_entry(i, k));
     __syncthreads();
@@ -428,7 +421,7 @@ __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const Par
             if (pro > left) pro = left;
             left -= pro;
             if (pro) rf.ensure(d.wpos + 10u);
-            for (; pro; --pro) *optr++ = (int16_t)d.one(rf, lut_s, k, kmask, dbg_lutmask);
+            for (; pro; --pro) *optr++ = (int16_t)d.one(rf, lut_s, k, kmask);
         }
         // ---- blocks of 16 samples: 8 steps of two, one 32-byte store (a full sector) -------------------
         uint32_t nblk = left >> 4;
@@ -450,19 +443,17 @@ __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const Par
                         pend1 = rf.load_chunk(rf.fetched + 4);
                         npend = 2;
                     }
-                    // the line two ahead: the request of a later block then hits L2
-                    if (rf.fetched + 68 <= rf.safe) prefetch_l2(rf.gbase + rf.fetched + 64);
                 }
                 uint4 o0, o1;
-                o0.x = d.two(rf, lut_s, k, kmask, dbg_lutmask);
-                o0.y = d.two(rf, lut_s, k, kmask, dbg_lutmask);
-                o0.z = d.two(rf, lut_s, k, kmask, dbg_lutmask);
-                o0.w = d.two(rf, lut_s, k, kmask, dbg_lutmask);
-                o1.x = d.two(rf, lut_s, k, kmask, dbg_lutmask);
-                o1.y = d.two(rf, lut_s, k, kmask, dbg_lutmask);
-                o1.z = d.two(rf, lut_s, k, kmask, dbg_lutmask);
-                o1.w = d.two(rf, lut_s, k, kmask, dbg_lutmask);
-                if (!dbg_nostore) stg_256(optr, o0, o1);
+                o0.x = d.two(rf, lut_s, k, kmask);
+                o0.y = d.two(rf, lut_s, k, kmask);
+                o0.z = d.two(rf, lut_s, k, kmask);
+                o0.w = d.two(rf, lut_s, k, kmask);
+                o1.x = d.two(rf, lut_s, k, kmask);
+                o1.y = d.two(rf, lut_s, k, kmask);
+                o1.z = d.two(rf, lut_s, k, kmask);
+                o1.w = d.two(rf, lut_s, k, kmask);
+                stg_256(optr, o0, o1);
                 optr += 16;
                 if (pend_at == rf.fetched) {                 // (an on-demand top-up may have overtaken it)
                     rf.store_chunk(rf.fetched, pend0);
@@ -473,7 +464,7 @@ __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const Par
         }
         // ---- epilogue: the last < 8 samples --------------------------------------------------------
         if (left) rf.ensure(d.wpos + 10u);
-        for (; left; --left) *optr++ = (int16_t)d.one(rf, lut_s, k, kmask, dbg_lutmask);
+        for (; left; --left) *optr++ = (int16_t)d.one(rf, lut_s, k, kmask);
 
         // the codes must end inside the last word of the record
         if (n) {
