@@ -32,8 +32,15 @@ namespace {
 // ------------------------------------------------------------------------------------
 // locate
 // ------------------------------------------------------------------------------------
-constexpr int kLocThreads   = 128;
-constexpr int kLocTileWords = 8192;          // 32 KB per stage, 2 stages
+// The stream has no index, only the chain cur += word[cur] + 1 (src/deltaRice.c:319-325), and a
+// hop through HBM costs a DRAM round trip.  One CTA per chunk therefore streams the chunk through
+// shared memory (cp.async, three tiles in flight) while ONE thread chases the chain at shared-
+// memory latency, writing the record positions of the tile to a list; the whole CTA then turns
+// the list into wave table entries.  Records longer than the pipeline are jumped over.
+constexpr int kLocThreads   = 256;
+constexpr int kLocTileWords = 8192;          // 32 KB per stage
+constexpr int kLocStages    = 3;
+constexpr int kLocListMax   = kLocTileWords;       // a record is at least its [nwords] word
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
@@ -46,8 +53,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // loads words [A, A+kLocTileWords) into `dst` ((comp + A) is 16-byte aligned; A may be negative
 // by up to 3 words when comp itself is not 16-byte aligned); words outside [0, limit) are skipped.
-__device__ __forceinline__ void locate_load_tile(uint32_t *dst, const uint32_t *comp, int64_t A,
-                                                 uint64_t limit)
+__device__ __forceinline__ void locate_load_tile(uint32_t *dst, const uint32_t *comp, int64_t A, uint64_t limit)
 {
     for (int v = threadIdx.x; v < kLocTileWords / 4; v += kLocThreads) {
         const int64_t w = A + 4ll * v;
@@ -62,10 +68,11 @@ __device__ __forceinline__ void locate_load_tile(uint32_t *dst, const uint32_t *
 
 __global__ void __launch_bounds__(kLocThreads) locate_kernel(const LocateParams p)
 {
-    extern __shared__ __align__(16) uint32_t stile[];   // 2 * kLocTileWords
+    extern __shared__ __align__(16) uint32_t stile[];   // kLocStages * kLocTileWords | list of kLocListMax
+    uint32_t *s_list = stile + kLocStages * kLocTileWords;      // tile-relative record positions
     __shared__ uint64_t s_cur;
-    __shared__ uint32_t s_wave;
-    __shared__ int s_done;
+    __shared__ uint32_t s_wave, s_cnt;
+    __shared__ int s_state;                              // 0 = next tile, 1 = done, 2 = jump to s_cur
     const uint32_t c = blockIdx.x;
     const uint64_t wb = p.chunk_word_off[c], we = p.chunk_word_off[c + 1];
     const uint64_t sb = p.chunk_sample_off[c], se = p.chunk_sample_off[c + 1];
@@ -83,64 +90,91 @@ __global__ void __launch_bounds__(kLocThreads) locate_kernel(const LocateParams 
         if (W == 0 && we != wb + 1) atomicOr(p.status, kErrStream);
         s_cur = wb + 1;
         s_wave = 0;
-        s_done = (W == 0);
+        s_state = (W == 0) ? 1 : 0;
     }
     __syncthreads();
-    if (s_done) return;
+    if (s_state == 1) return;
 
     // misalignment of the global address: tiles start at word indices A with (comp + A) 16-byte aligned
     const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(p.comp) >> 2) & 3u);
     auto align_down = [mis](uint64_t w) { return (int64_t)((w + mis) & ~3ull) - (int64_t)mis; };
 
-    int64_t A = align_down(wb + 1);
-    int buf = 0;
-    locate_load_tile(stile, p.comp, A, we);
-    cp_async_commit();
+    int64_t A = align_down(wb + 1);                      // first word of the oldest tile in flight
+    int head = 0;                                        // its stage
+    auto refill_all = [&]() {
+#pragma unroll
+        for (int sidx = 0; sidx < kLocStages; ++sidx) {
+            const int64_t At = A + (int64_t)sidx * kLocTileWords;
+            if ((uint64_t)(At < 0 ? 0 : At) < we) locate_load_tile(stile + ((head + sidx) % kLocStages) * kLocTileWords, p.comp, At, we);
+            cp_async_commit();
+        }
+    };
+    refill_all();
     while (true) {
-        // prefetch the sequentially next tile into the other buffer
-        const int64_t An = A + kLocTileWords;
-        if ((uint64_t)An < we) locate_load_tile(stile + (buf ^ 1) * kLocTileWords, p.comp, An, we);
-        cp_async_commit();
-        cp_async_wait<1>();
+        cp_async_wait<kLocStages - 1>();                 // the oldest tile has landed
         __syncthreads();
         if (threadIdx.x == 0) {
-            const uint32_t *t = stile + buf * kLocTileWords;
+            const uint32_t *t = stile + head * kLocTileWords;
             uint64_t cur = s_cur;
-            uint32_t w = s_wave;
+            uint32_t w = s_wave, cnt = 0;
             const uint64_t tile_end = (uint64_t)(A + kLocTileWords);
-            while (w < W && cur < tile_end && cur < we) {
-                const uint32_t nw = t[(int64_t)cur - A];
-                const uint64_t s0 = (uint64_t)w * Lw;
-                p.wave_in[g0 + w] = cur;
-                p.wave_out[g0 + w] = sb + s0;
-                p.wave_n[g0 + w] = (uint32_t)((total - s0) < Lw ? (total - s0) : Lw);
-                cur += (uint64_t)nw + 1;
-                ++w;
+            const uint64_t stop = tile_end < we ? tile_end : we;
+            if (cur < stop) {
+                // tile-relative 32-bit chase: the dependent chain is one LDS + one add per hop
+                uint32_t rel = (uint32_t)((int64_t)cur - A);
+                const uint32_t stop_rel = (uint32_t)((int64_t)stop - A);
+                const uint32_t wleft = W - w;
+                while (cnt < wleft && rel < stop_rel) {
+                    s_list[cnt++] = rel;
+                    rel += t[rel] + 1u;
+                }
+                w += cnt;
+                cur = (uint64_t)(A + (int64_t)rel);
             }
             s_cur = cur;
-            s_wave = w;
+            s_cnt = cnt;
+            int state = 0;
             if (w == W) {
                 if (cur != we) atomicOr(p.status, kErrStream);
-                s_done = 1;
+                state = 1;
             } else if (cur >= we) {
                 atomicOr(p.status, kErrStream);
                 // neutralise the waves that could not be located
-                for (; w < W; ++w) { p.wave_in[g0 + w] = wb; p.wave_out[g0 + w] = sb; p.wave_n[g0 + w] = 0; }
-                s_done = 1;
+                for (uint32_t x = w; x < W; ++x) { p.wave_in[g0 + x] = wb; p.wave_out[g0 + x] = sb; p.wave_n[g0 + x] = 0; }
+                state = 1;
+            } else if (cur >= (uint64_t)(A + (int64_t)kLocStages * kLocTileWords)) {
+                state = 2;                               // a record longer than everything in flight
             }
+            s_state = state;
         }
         __syncthreads();
-        if (s_done) break;
-        const uint64_t cur = s_cur;
-        if (cur < (uint64_t)(An + kLocTileWords)) {
-            A = An;                           // the prefetched tile is the one we need
-            buf ^= 1;
-        } else {                              // long record: jump, drop the prefetch
+        // the tile's records -> wave table, by everybody
+        {
+            const uint32_t cnt = s_cnt, w0 = s_wave;
+            for (uint32_t i = threadIdx.x; i < cnt; i += kLocThreads) {
+                const uint32_t w = w0 + i;
+                const uint64_t s0 = (uint64_t)w * Lw;
+                p.wave_in[g0 + w] = (uint64_t)(A + (int64_t)s_list[i]);
+                p.wave_out[g0 + w] = sb + s0;
+                p.wave_n[g0 + w] = (uint32_t)((total - s0) < Lw ? (total - s0) : Lw);
+            }
+        }
+        const int state = s_state;
+        __syncthreads();                                 // list and tile are free again
+        if (threadIdx.x == 0) s_wave += s_cnt;
+        if (state == 1) break;
+        if (state == 2) {                                // restart the pipeline at the record's header
             cp_async_wait<0>();
             __syncthreads();
-            A = align_down(cur);
-            locate_load_tile(stile + buf * kLocTileWords, p.comp, A, we);
+            A = align_down(s_cur);
+            head = 0;
+            refill_all();
+        } else {                                         // reuse the stage for the tile after the ones in flight
+            const int64_t An = A + (int64_t)kLocStages * kLocTileWords;
+            if ((uint64_t)An < we) locate_load_tile(stile + head * kLocTileWords, p.comp, An, we);
             cp_async_commit();
+            A += kLocTileWords;
+            head = (head + 1) % kLocStages;
         }
     }
     cp_async_wait<0>();
@@ -545,7 +579,7 @@ int launch_locate(const LocateParams &p, cudaStream_t st)
 {
     if (p.nchunks == 0) return 0;
     static bool attr_set = false;
-    const size_t smem = 2 * kLocTileWords * sizeof(uint32_t);
+    const size_t smem = (size_t)(kLocStages * kLocTileWords + kLocListMax) * sizeof(uint32_t);
     if (!attr_set) {
         cudaFuncSetAttribute(locate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
