@@ -501,8 +501,8 @@ __device__ __forceinline__ uint32_t encode_wave(const int16_t *wave, uint32_t n,
 // done with it.
 constexpr int kRing = 3;
 
-template <int K>
-__global__ void __launch_bounds__((kEncWarps + 1) * 32)
+template <int K, int MINB>
+__global__ void __launch_bounds__((kEncWarps + 1) * 32, MINB)
 encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint32_t ntiles)
 {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -510,21 +510,20 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
     __shared__ uint32_t s_mine[kRing][kEncWarps];        // words each wave contributes
     __shared__ uint32_t s_cnt[kRing];                    // workers that have reported
     __shared__ uint32_t s_total[kRing];
-    __shared__ volatile uint32_t s_ready[kRing];         // = it + 1 once s_total is valid
     __shared__ uint64_t s_off[kRing];                    // tile's exclusive word offset
     __shared__ volatile uint32_t s_flag[kRing];          // = it + 1 once s_off is valid
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool control = warp == kEncWarps;
 
-    if (threadIdx.x < kRing) { s_flag[threadIdx.x] = 0; s_ready[threadIdx.x] = 0; s_cnt[threadIdx.x] = 0; }
+    if (threadIdx.x < kRing) { s_flag[threadIdx.x] = 0; s_cnt[threadIdx.x] = 0; }
     if (threadIdx.x == 0) s_tile[0] = atomicAdd(p.ticket, 1u);
     __syncthreads();
 
     if (control) {
         for (uint32_t it = 0;; ++it) {
             const int slot = it % kRing;
-            while (s_ready[slot] != it + 1) __nanosleep(400);
-            __threadfence_block();
+            // sleeps on a named barrier (one per ring slot) until the tile's last worker arrives
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + slot) : "memory");
             const uint32_t tile = s_tile[slot];
             if (tile >= ntiles) break;
             const uint64_t mine = s_total[slot];
@@ -572,6 +571,7 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
             // next tile: taken as late as possible so that tiles start in ticket order; the
             // atomic's latency hides behind the copy-out below
             if (threadIdx.x == 0) next_ticket = atomicAdd(p.ticket, 1u);
+            bool last = false;
             if (lane == 0) {
                 s_mine[slot][warp] = mine;
                 __threadfence_block();
@@ -585,12 +585,14 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
                     s_total[slot] = total;
                     s_cnt[slot] = 0;
                     __threadfence_block();
-                    s_ready[slot] = it + 1;
+                    last = true;
                 }
             }
-        } else if (threadIdx.x == 0) {
+            if (__shfl_sync(0xffffffffu, last, 0))           // wakes the control warp
+                asm volatile("bar.arrive %0, 64;" ::"r"(2 + slot) : "memory");
+        } else if (warp == 0) {
             __threadfence_block();
-            s_ready[slot] = it + 1;                          // lets the control warp see the end
+            asm volatile("bar.arrive %0, 64;" ::"r"(2 + slot) : "memory");   // lets the control warp see the end
         }
         // ---- copy out the wave of the previous iteration ------------------------------------
         if (have_prev) {
@@ -884,19 +886,6 @@ encode_multi_kernel(const EncodeParams p)
 
 int g_num_sms = 0;
 
-uint32_t stage_cap_words()
-{
-    static uint32_t v = 0;
-    if (!v) {
-        const char *e = getenv("DRICE_ENC_STAGE_WORDS");
-        long w = e ? atol(e) : 1600;
-        if (w < 64) w = 64;
-        if (w > 12000) w = 12000;
-        v = (uint32_t)w;
-    }
-    return v;
-}
-
 template <int K>
 int launch_k(const EncodeParams &p, uint32_t max_wave_len, cudaStream_t st)
 {
@@ -911,26 +900,37 @@ int launch_k(const EncodeParams &p, uint32_t max_wave_len, cudaStream_t st)
         encode_multi_kernel<K><<<p.nwaves, kEncMaxThreads, smem_multi, st>>>(p);
         return 1;
     }
-    // per-warp staging: the worst case of the longest wave when it is affordable, else a cap
-    // (a wave that outgrows it is packed straight into its record in HBM)
-    uint32_t stage = (25u * max_wave_len + 31u) / 32u + 24u;
-    if (stage > stage_cap_words()) stage = stage_cap_words();
+    // per-warp staging (two buffers per worker warp): room for ~10 bits per sample, at most the
+    // worst case; a wave that outgrows it is packed straight into its record in HBM.  Short
+    // waves leave room for three CTAs per SM (72 registers), longer ones run two (more registers).
+    const uint32_t worst = (25u * max_wave_len + 31u) / 32u + 24u;
+    uint32_t stage = (10u * max_wave_len + 31u) / 32u + 24u;
+    const char *e = getenv("DRICE_ENC_STAGE_WORDS");
+    const bool three = !e && stage <= 1120u;
+    if (e) stage = (uint32_t)atol(e);
+    else if (three) stage = stage < 1088u ? stage : 1088u;
+    else stage = 1600u;
+    if (stage > worst) stage = worst;
+    if (stage < 64u) stage = 64u;
     stage = (stage + 3u) & ~3u;
     const size_t smem = (size_t)stage * 2 * kEncWarps * sizeof(uint32_t);   // two buffers per worker warp
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(encode_tile_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(encode_tile_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        attr_set = true;
-    }
     const int nthreads = (kEncWarps + 1) * 32;
-    int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encode_tile_kernel<K>, nthreads, smem);
-    if (occ < 1) occ = 1;
     const uint32_t ntiles = (p.nwaves + kEncWarps - 1) / kEncWarps;
-    uint32_t grid = (uint32_t)(g_num_sms * occ);
-    if (grid > ntiles) grid = ntiles;
-    encode_tile_kernel<K><<<grid, nthreads, smem, st>>>(p, stage, ntiles);
+    auto launch = [&](auto kernel, bool &attr_set) {
+        if (!attr_set) {
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            attr_set = true;
+        }
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, nthreads, smem);
+        if (occ < 1) occ = 1;
+        uint32_t grid = (uint32_t)(g_num_sms * occ);
+        if (grid > ntiles) grid = ntiles;
+        kernel<<<grid, nthreads, smem, st>>>(p, stage, ntiles);
+    };
+    static bool attr3 = false, attr2 = false;            // per K (this function is a template)
+    if (three) launch(encode_tile_kernel<K, 3>, attr3); else launch(encode_tile_kernel<K, 2>, attr2);
     return 1;
 }
 
