@@ -186,21 +186,34 @@ __global__ void __launch_bounds__(kLocThreads) locate_kernel(const LocateParams 
 // Rice parsing is a serial chain per wave (a code's length is only known once its unary
 // prefix has been read), so the parallelism is across waves: one LANE per wave, a warp takes
 // 32 consecutive waves per ticket.  The kernel is bound by issue slots and by the shared-memory
-// (MIO) pipe, so the inner loop is built to touch shared memory as little as possible:
-//   * one code = one lookup: the next 12 stream bits index a shared-memory table built for the
-//     launch's k whose 4-byte entry is (delta << 16 | bits consumed); escapes and codes longer
-//     than the window miss (entry 0) and take a count-leading-zeros path;
-//   * a step decodes exactly TWO samples (two chained lookups in a 96-bit register window), so
-//     every lane of the warp advances in lock step and the two 16-bit results pack into one
-//     register; four steps fill a 16-byte block that the lane stores straight to HBM - there is
-//     no shared-memory staging of the output at all;
-//   * the compressed words reach the lane through a private 16-word ring in shared memory
-//     ([word][lane], bank = lane: conflict free), refilled with one 16-byte load per block that is
-//     requested a block ahead.
-constexpr int kLutBits     = 12;
-constexpr int kLutSize     = 1 << kLutBits;
-constexpr int kRingWords   = 32;                 // compressed words per lane (4 KB per warp)
-constexpr int kParseMaxWarps = 17;               // per CTA; two CTAs per SM
+// (MIO) pipe, so the inner loop is built around instructions and wavefronts per sample:
+//   * one code = one lookup: the next W stream bits index a shared-memory table built for the
+//     launch's k whose 4-byte entry is (delta << 16 | bits consumed).  The lane's whole decoder
+//     state is ONE register S = (running sample << 16 | bit position in its ring), so a code
+//     costs a single add: S += entry (the inverse delta and the bit pointer advance together;
+//     the low half is folded every 16 samples so that it never carries into the sample);
+//   * the table is replicated R times (entry index * R + lane % R): lanes that share a bank
+//     only conflict within their group of 32 / R lanes, which cuts the wavefronts per lookup
+//     from ~3.7 (random) to ~2 (R = 8, k = 2) - W and R are chosen per k to fill 32 KB;
+//   * four codes per window: a 64-bit window is rebuilt from three ring words addressed by the
+//     bit position (no window rotation, no per-sample refill test), then shifted by each code's
+//     length; the four results are checked for a miss ONCE (min of the entries == 0: escapes and
+//     codes longer than the window), in which case the group is redone code by code with
+//     count-leading-zeros;
+//   * every lane of the warp advances in lock step; 16 samples pack into one 32-byte sector that
+//     the lane stores straight to HBM - there is no shared-memory staging of the output;
+//   * the compressed words reach the lane through a private 32-word ring in shared memory
+//     ([word][lane], bank = lane: conflict free; rows 32/33 mirror rows 0/1 so that a window never
+//     wraps), refilled with one 32-byte load (a full sector) that is requested a block ahead.
+constexpr int      kRingWords  = 32;                 // compressed words per lane
+constexpr int      kRingRows   = kRingWords + 2;     // + mirror of rows 0 and 1
+constexpr uint32_t kRingBytes  = kRingRows * 128u;   // per warp
+constexpr int      kChunkWords = 8;                  // one 32-byte sector per refill
+constexpr uint32_t kLutBytes   = 32768;              // table incl. replication, aligned to its size
+constexpr int      kLutMaxBits = 12;
+constexpr uint32_t kAhead      = 16;                 // ring words guaranteed ahead at a block start:
+                                                     // 16 escapes (400 bits) + the 3-word window
+constexpr int kParseMaxWarps = 17;                   // per CTA; two CTAs per SM
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
@@ -215,15 +228,25 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+template <int OFF>
+__device__ __forceinline__ uint32_t lds32o(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v)
 {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint4 ldg_cg_u4(const void *p)
+struct Chunk8 { uint4 a, b; };
+// one full 32-byte sector, L2 only: every lane streams its own record
+__device__ __forceinline__ Chunk8 ldg_cg_256(const void *p)
 {
-    uint4 r;
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"      // L2 only: every lane streams its own record
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    Chunk8 r;
+    asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w)
+                 : "l"(p));
     return r;
 }
 // one full 32-byte sector per lane: partial-sector stores make L2 read the sector from DRAM first
@@ -232,83 +255,77 @@ __device__ __forceinline__ void stg_256(void *p, const uint4 &a, const uint4 &b)
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
                  "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
 }
-// table entry for the kLutBits bits `idx` (MSB = next stream bit), Rice parameter 2^k:
+// window width / replication of the table for Rice parameter 2^k: the longest non-escape code
+// has 8 + k bits; what the 32 KB do not need for the window goes into replication
+__host__ __device__ __forceinline__ int lut_bits_for(int k) { return k + 8 < kLutMaxBits ? k + 8 : kLutMaxBits; }
+// table entry for the W bits `idx` (MSB = next stream bit), Rice parameter 2^k:
 // (delta << 16) | bits consumed for the one complete non-escape code the window starts with
 // (src/deltaRice.c:161-177), 0 if there is none.
-__device__ __forceinline__ uint32_t make_lut_entry(uint32_t idx, int k)
+__device__ __forceinline__ uint32_t make_lut_entry(uint32_t idx, int k, int W)
 {
-    const uint32_t win = idx << (32 - kLutBits);
+    const uint32_t win = idx << (32 - W);
     const uint32_t q = win ? (uint32_t)__clz(win) : 32u;
     const uint32_t len = q + 1 + (uint32_t)k;
-    if (q >= kEscapeQuotient || len > (uint32_t)kLutBits) return 0u;
+    if (q >= kEscapeQuotient || len > (uint32_t)W) return 0u;
     const uint32_t r = (win >> (32 - len)) & ((1u << k) - 1u);
     const uint32_t u = (q << k) | r;
     const int d = (u & 1u) ? -(int)((u + 1) >> 1) : (int)(u >> 1);
     return ((uint32_t)d << 16) | len;
 }
 
-// where a lane's compressed words come from (one wave)
+// where a lane's compressed words come from (one wave): the ring holds words [.., fetched) of the
+// record, counted from `ring word 0` = the 32-byte aligned block that holds the first code word
 struct RingFeed {
-    const uint32_t *gbase;      // 16-byte aligned address of chunk 0
-    const uint32_t *comp_al;    // aligned address at or below the stream
-    uint64_t base_al, lim_al;   // chunk 0 / end of the stream, words from comp_al
+    const uint32_t *gbase;      // 32-byte aligned address of ring word 0
+    const uint32_t *comp_al;    // 32-byte aligned address at or below the stream
+    uint64_t base_al, lim_al;   // ring word 0 / end of the stream, words from comp_al
     uint32_t mis;               // words between comp_al and the stream
-    uint32_t safe;              // chunks [0, safe) need no bounds checks
-    uint32_t ring_b;            // shared address of the lane's ring word 0 (region aligned to its size)
-    uint32_t fetched;           // words in the ring so far (multiple of 4), from chunk 0
+    uint32_t safe;              // ring words [0, safe) need no bounds checks
+    uint32_t ring_b;            // shared address of the lane's ring row 0
+    uint32_t fetched;           // words in the ring so far (multiple of 8)
 
-    __device__ __forceinline__ uint4 load_chunk(uint32_t at) const
+    __device__ __forceinline__ Chunk8 load_chunk(uint32_t at) const
     {
-        if (at + 4 <= safe) return ldg_cg_u4(gbase + at);
+        if (at + kChunkWords <= safe) return ldg_cg_256(gbase + at);
         const uint64_t aw = base_al + at;
-        uint32_t e[4];
+        uint32_t e[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) e[i] = (aw + i >= mis && aw + i < lim_al) ? comp_al[aw + i] : 0u;
-        return make_uint4(e[0], e[1], e[2], e[3]);
+        for (int i = 0; i < 8; ++i) e[i] = (aw + i >= mis && aw + i < lim_al) ? comp_al[aw + i] : 0u;
+        Chunk8 c;
+        c.a = make_uint4(e[0], e[1], e[2], e[3]);
+        c.b = make_uint4(e[4], e[5], e[6], e[7]);
+        return c;
     }
-    __device__ __forceinline__ void store_chunk(uint32_t at, const uint4 &c) const
+    __device__ __forceinline__ void store_chunk(uint32_t at, const Chunk8 &c) const
     {
-        const uint32_t ad = ((at << 7) & ((kRingWords << 7) - 128u)) | ring_b;
-        sts32(ad, c.x); sts32(ad + 128, c.y); sts32(ad + 256, c.z); sts32(ad + 384, c.w);
-    }
-    __device__ __forceinline__ uint32_t word(uint32_t x) const
-    {
-        return lds32(((x << 7) & ((kRingWords << 7) - 128u)) | ring_b);
-    }
-    // synchronous top-up until `need` words (from chunk 0) are in the ring
-    __device__ __forceinline__ void ensure(uint32_t need)
-    {
-        while (fetched < need) {
-            store_chunk(fetched, load_chunk(fetched));
-            fetched += 4;
+        const uint32_t row = at & (kRingWords - 1);
+        const uint32_t ad = ring_b + (row << 7);
+        sts32(ad, c.a.x); sts32(ad + 128, c.a.y); sts32(ad + 256, c.a.z); sts32(ad + 384, c.a.w);
+        sts32(ad + 512, c.b.x); sts32(ad + 640, c.b.y); sts32(ad + 768, c.b.z); sts32(ad + 896, c.b.w);
+        if (row == 0) {                                      // mirror rows for windows that start in rows 30/31
+            sts32(ad + kRingWords * 128, c.a.x);
+            sts32(ad + kRingWords * 128 + 128, c.a.y);
         }
     }
 };
 
-// decoder state of one lane: a 96-bit window w0:w1:w2 over the stream
+// decoder state of one lane
 struct LaneDec {
-    uint32_t w0, w1, w2;
-    uint32_t bit;           // bits of w0 already consumed (< 32 between steps)
-    uint32_t wpos;          // position of w0 (words from the wave's chunk 0)
-    uint32_t acc;           // running sample (low 16 bits count)
+    uint32_t S;             // (running sample << 16) | bit position in the ring (bits 5..9 = ring row)
+    uint32_t tb;            // bits folded out of S's low half (multiple of 1024)
     bool     bad;
 
-    __device__ __forceinline__ void advance(RingFeed &rf)
+    // shared address of the ring row that holds the current bit
+    __device__ __forceinline__ uint32_t row_addr(uint32_t ring_b) const { return ((S & 0x3E0u) << 2) + ring_b; }
+
+    // one code through count-leading-zeros (src/deltaRice.c:154-177): escapes, codes the table
+    // does not hold, and the first / last few samples of a wave
+    __device__ __forceinline__ void one(uint32_t ring_b, int k, uint32_t kmask)
     {
-        if (bit >= 32u) {
-            bit -= 32u;
-            ++wpos;
-            w0 = w1;
-            w1 = w2;
-            w2 = rf.word(wpos + 2);
-        }
-    }
-    // one code that the table does not hold, through count-leading-zeros (src/deltaRice.c:154-177);
-    // `win` = the 32 stream bits at the current position.  Returns the delta.
-    __device__ __forceinline__ uint32_t slow_code(uint32_t win, RingFeed &rf, int k, uint32_t kmask, uint32_t &len)
-    {
+        const uint32_t a = row_addr(ring_b);
+        const uint32_t win = __funnelshift_l(lds32o<128>(a), lds32o<0>(a), S);
         const uint32_t q = __clz(win);
-        uint32_t u;
+        uint32_t u, len;
         if (q >= kEscapeQuotient) {
             bad |= (q > kEscapeQuotient);
             u = (win >> 7) & 0xFFFFu;
@@ -317,91 +334,52 @@ struct LaneDec {
             len = q + 1 + (uint32_t)k;
             u = (q << k) | ((win >> (32u - len)) & kmask);
         }
-        // the periodic refill only covers a block of table-path codes (<= 12 bits each): after an
-        // escape make sure the rest of the block (<= 6 more words + the window) is in the ring
-        rf.ensure(wpos + 12u);
         const uint32_t h = u >> 1;
-        return (u & 1u) ? ~h : h;
+        const uint32_t d = (u & 1u) ? ~h : h;
+        S += (d << 16) + len;
     }
-    // decodes ONE sample (prologue / epilogue of a wave); bit < 32 on entry and on exit
-    __device__ __forceinline__ uint32_t one(RingFeed &rf, uint32_t lut_s, int k, uint32_t kmask)
+    // keeps the low half of S below 1024 + one block, so that it never carries into the sample
+    __device__ __forceinline__ void fold()
     {
-        const uint32_t win = __funnelshift_l(w1, w0, bit);
-        const uint32_t e = lds32(lut_s + ((win >> (32 - kLutBits - 2)) & ((kLutSize - 1) << 2)));
-        uint32_t dl, len;
-        if (e) {
-            dl = (uint32_t)((int32_t)e >> 16);
-            len = e & 31u;
-        } else {
-            dl = slow_code(win, rf, k, kmask, len);
-        }
-        acc += dl;
-        bit += len;
-        advance(rf);
-        return acc & 0xFFFFu;
+        tb += S & 0xFC00u;
+        S &= 0xFFFF03FFu;
     }
-    // decodes TWO samples, packed lo | hi << 16; bit < 32 on entry and on exit
-    __device__ __forceinline__ uint32_t two(RingFeed &rf, uint32_t lut_s, int k, uint32_t kmask)
-    {
-        const uint32_t win1 = __funnelshift_l(w1, w0, bit);
-        const uint32_t e1 = lds32(lut_s + ((win1 >> (32 - kLutBits - 2)) & ((kLutSize - 1) << 2)));
-        uint32_t d1, len1;
-        if (e1) {
-            d1 = (uint32_t)((int32_t)e1 >> 16);
-            len1 = e1 & 31u;
-        } else {
-            d1 = slow_code(win1, rf, k, kmask, len1);
-            bit += len1;
-            advance(rf);                 // an escape may cross a word: keep the second window in reach
-            len1 = 0;
-        }
-        const uint32_t b1 = bit + len1;                     // < 44
-        const bool hiw = b1 >= 32u;
-        const uint32_t win2 = __funnelshift_l(hiw ? w2 : w1, hiw ? w1 : w0, b1);
-        const uint32_t e2 = lds32(lut_s + ((win2 >> (32 - kLutBits - 2)) & ((kLutSize - 1) << 2)));
-        const uint32_t y1 = acc + d1;
-        uint32_t d2, len2;
-        if (e2) {
-            d2 = (uint32_t)((int32_t)e2 >> 16);
-            len2 = e2 & 31u;
-        } else {
-            bit = b1;
-            advance(rf);
-            d2 = slow_code(__funnelshift_l(w1, w0, bit), rf, k, kmask, len2);
-            bit += len2;
-            advance(rf);
-            acc = y1 + d2;
-            return prmt(y1, acc, 0x5410);
-        }
-        acc = y1 + d2;
-        bit = b1 + len2;                                    // < 56
-        advance(rf);
-        return prmt(y1, acc, 0x5410);
-    }
+    __device__ __forceinline__ uint32_t bits() const { return tb + (S & 0xFFFFu); }   // from ring word 0
 };
 
 __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const ParseParams p)
 {
     extern __shared__ __align__(16) uint32_t dsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // shared layout: [pad to 2 KB] one 2 KB ring per warp | table
+    // shared layout: the table sits at the first 32 KB boundary of the CTA's shared window (its
+    // address is OR-ed, not added); the rings of the first warps fill the gap below it, the
+    // others follow it
     const uint32_t dsm_s = (uint32_t)__cvta_generic_to_shared(dsm);
     const uint32_t nwarps = blockDim.x >> 5;
-    const uint32_t rings_s = (dsm_s + kRingWords * 128u - 1u) & ~(kRingWords * 128u - 1u);
-    const uint32_t lut_s = rings_s + nwarps * (kRingWords * 128u);
-    if (lut_s + kLutSize * 4u > dsm_s + p.smem_bytes) {     // launcher and kernel disagree on the layout
+    const uint32_t lut_s = (dsm_s + kLutBytes - 1u) & ~(kLutBytes - 1u);
+    const uint32_t nbelow = (lut_s - dsm_s) / kRingBytes;   // rings that fit below the table
+    const uint32_t nabove = nwarps > nbelow ? nwarps - nbelow : 0u;
+    if (lut_s + kLutBytes + nabove * kRingBytes > dsm_s + p.smem_bytes) {     // launcher and kernel disagree on the layout
         if (threadIdx.x == 0) atomicOr(p.status, kErrStream);
         return;
     }
+    const uint32_t ring_warp_s = (uint32_t)warp < nbelow ? dsm_s + (uint32_t)warp * kRingBytes
+                                                         : lut_s + kLutBytes + ((uint32_t)warp - nbelow) * kRingBytes;
     const int k = p.k;
     const uint32_t kmask = (1u << k) - 1u;
-
-    for (uint32_t i = threadIdx.x; i < (uint32_t)kLutSize; i += blockDim.x) sts32(lut_s + 4u * i, make_lut_entry(i, k));
+    const int W = lut_bits_for(k);
+    const int rsh = 13 - W;                                  // log2(replicas): 2^W entries * 4 B * R = 32 KB
+    for (uint32_t i = threadIdx.x; i < kLutBytes / 4u; i += blockDim.x) sts32(lut_s + 4u * i, make_lut_entry(i >> rsh, k, W));
     __syncthreads();
+    // byte offset of a table entry = (window >> ish) & imask, | the lane's replica
+    const uint32_t ish = (uint32_t)(32 - W - 2 - rsh);       // = 17 for every W
+    uint32_t imask = ((1u << W) - 1u) << (2 + rsh);
+    asm volatile("mov.u32 %0, %0;" : "+r"(imask));          // keep it in a register (not recomputed per block)
+    const uint32_t lutl = lut_s | (((uint32_t)lane & ((1u << rsh) - 1u)) << 2);
 
-    // compressed words are fetched as 16-byte chunks that are aligned in memory: positions are
-    // words relative to the aligned address at or below p.comp
-    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(p.comp) >> 2) & 3u);
+    // compressed words are fetched as 32-byte sectors: positions are words relative to the
+    // 32-byte aligned address at or below p.comp
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(p.comp) >> 2) & 7u);
     const uint32_t *comp_al = p.comp - mis;
     const uint64_t lim_al = p.comp_words + mis;             // end of the stream, aligned-relative
     const uint32_t ngroups = (p.nwaves + 31u) / 32u;
@@ -420,90 +398,120 @@ __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const Par
         int16_t *optr = p.out + obase;
 
         RingFeed rf;
-        rf.base_al = (rec + 1 + mis) & ~3ull;               // aligned-relative index of the chunk holding the first code word
+        rf.base_al = (rec + 1 + mis) & ~7ull;               // aligned-relative index of the sector holding the first code word
         rf.gbase = comp_al + rf.base_al;
         rf.comp_al = comp_al;
         rf.lim_al = lim_al;
         rf.mis = mis;
         rf.safe = (rf.base_al >= mis)
-            ? (uint32_t)(lim_al - rf.base_al > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : ((lim_al - rf.base_al) & ~3ull)) : 0u;
-        rf.ring_b = rings_s + warp * (kRingWords * 128u) + lane * 4u;
+            ? (uint32_t)(lim_al - rf.base_al > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : ((lim_al - rf.base_al) & ~7ull)) : 0u;
+        rf.ring_b = ring_warp_s + lane * 4u;
         rf.fetched = 0;
+        const uint32_t ring_b = rf.ring_b;
 
         LaneDec d;
-        d.wpos = (uint32_t)((rec + 1 + mis) - rf.base_al);
-        d.bit = 0; d.acc = 0; d.bad = false; d.w0 = d.w1 = d.w2 = 0;
+        const uint32_t start_bits = (uint32_t)((rec + 1 + mis) - rf.base_al) << 5;
+        d.S = start_bits;
+        d.tb = 0;
+        d.bad = false;
         __syncwarp();
         if (n) {
 #pragma unroll
-            for (int c = 0; c < kRingWords / 4; c += 2) {
-                const uint4 c0 = rf.load_chunk(4u * c), c1 = rf.load_chunk(4u * c + 4);
-                rf.store_chunk(4u * c, c0);
-                rf.store_chunk(4u * c + 4, c1);
+            for (int c = 0; c < kRingWords; c += 2 * kChunkWords) {
+                const Chunk8 c0 = rf.load_chunk(c), c1 = rf.load_chunk(c + kChunkWords);
+                rf.store_chunk(c, c0);
+                rf.store_chunk(c + kChunkWords, c1);
             }
             rf.fetched = kRingWords;
-            d.w0 = rf.word(d.wpos);
-            d.w1 = rf.word(d.wpos + 1);
-            d.w2 = rf.word(d.wpos + 2);
         }
 
         // ---- prologue: single samples up to the first 32-byte boundary of the output --------------
+        // (<= 15 codes of <= 25 bits: inside the first fill)
         uint32_t left = n;
         {
             const uint32_t a = (uint32_t)((reinterpret_cast<uintptr_t>(optr) >> 1) & 15u);
             uint32_t pro = (16u - a) & 15u;
             if (pro > left) pro = left;
             left -= pro;
-            if (pro) rf.ensure(d.wpos + 10u);
-            for (; pro; --pro) *optr++ = (int16_t)d.one(rf, lut_s, k, kmask);
+            for (; pro; --pro) {
+                d.one(ring_b, k, kmask);
+                *optr++ = (int16_t)(d.S >> 16);
+            }
         }
-        // ---- blocks of 16 samples: 8 steps of two, one 32-byte store (a full sector) -------------------
+        // ---- blocks of 16 samples: 4 groups of four codes, one 32-byte store (a full sector) -------
         uint32_t nblk = left >> 4;
         left &= 15u;
         const uint32_t maxblk = __reduce_max_sync(0xffffffffu, nblk);
-        for (uint32_t b = 0; b < maxblk; ++b) {
+        Chunk8 pend;
+        pend.a = pend.b = make_uint4(0, 0, 0, 0);
+        bool have_pend = false;
+        for (uint32_t b = 0; b <= maxblk; ++b) {
+            // the last pass (b == nblk) only tops the ring up for the epilogue
+            if (b <= nblk && n) {
+                d.fold();
+                const uint32_t cons = d.bits() >> 5;         // ring word of the current bit
+                if (have_pend) {
+                    rf.store_chunk(rf.fetched, pend);
+                    rf.fetched += kChunkWords;
+                }
+                while (rf.fetched < cons + kAhead) {         // escape-heavy data outruns one sector per block
+                    rf.store_chunk(rf.fetched, rf.load_chunk(rf.fetched));
+                    rf.fetched += kChunkWords;
+                }
+                have_pend = (b < nblk) && (rf.fetched + kChunkWords <= (cons & ~(uint32_t)(kChunkWords - 1)) + kRingWords);
+                if (have_pend) pend = rf.load_chunk(rf.fetched);
+            }
             if (b < nblk) {
-                // ring refill: the chunks requested now go in after the block's steps (a block uses at
-                // most 6 words through the table; longer codes top up on demand)
-                rf.ensure(d.wpos + 10u);
-                uint4 pend0 = make_uint4(0, 0, 0, 0), pend1 = pend0;
-                uint32_t pend_at = 0xffffffffu, npend = 0;
-                const uint32_t room = (d.wpos & ~3u) + kRingWords - rf.fetched;
-                if (room >= 4) {
-                    pend_at = rf.fetched;
-                    pend0 = rf.load_chunk(rf.fetched);
-                    npend = 1;
-                    if (room >= 8) {
-                        pend1 = rf.load_chunk(rf.fetched + 4);
-                        npend = 2;
+                uint32_t o[8];
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                    const uint32_t S0 = d.S;
+                    const uint32_t a = d.row_addr(ring_b);
+                    const uint32_t w0 = lds32o<0>(a), w1 = lds32o<128>(a), w2 = lds32o<256>(a);
+                    uint32_t hi = __funnelshift_l(w1, w0, S0);
+                    uint32_t lo = __funnelshift_l(w2, w1, S0);
+                    const uint32_t e1 = lds32(((hi >> ish) & imask) | lutl);
+                    const uint32_t S1 = S0 + e1;
+                    hi = __funnelshift_l(lo, hi, e1);
+                    lo = __funnelshift_l(0u, lo, e1);
+                    const uint32_t e2 = lds32(((hi >> ish) & imask) | lutl);
+                    const uint32_t S2 = S1 + e2;
+                    hi = __funnelshift_l(lo, hi, e2);
+                    const uint32_t e3 = lds32(((hi >> ish) & imask) | lutl);
+                    const uint32_t S3 = S2 + e3;
+                    hi = __funnelshift_l(0u, hi, e3);
+                    const uint32_t e4 = lds32(((hi >> ish) & imask) | lutl);
+                    const uint32_t S4 = S3 + e4;
+                    uint32_t r01 = prmt(S1, S2, 0x7632), r23 = prmt(S3, S4, 0x7632);
+                    d.S = S4;
+                    if (min(min(e1, e2), min(e3, e4)) == 0u) {       // an escape / a code longer than the window
+                        d.S = S0;
+                        d.one(ring_b, k, kmask);
+                        const uint32_t t1 = d.S;
+                        d.one(ring_b, k, kmask);
+                        r01 = prmt(t1, d.S, 0x7632);
+                        d.one(ring_b, k, kmask);
+                        const uint32_t t3 = d.S;
+                        d.one(ring_b, k, kmask);
+                        r23 = prmt(t3, d.S, 0x7632);
                     }
+                    o[2 * gq] = r01;
+                    o[2 * gq + 1] = r23;
                 }
-                uint4 o0, o1;
-                o0.x = d.two(rf, lut_s, k, kmask);
-                o0.y = d.two(rf, lut_s, k, kmask);
-                o0.z = d.two(rf, lut_s, k, kmask);
-                o0.w = d.two(rf, lut_s, k, kmask);
-                o1.x = d.two(rf, lut_s, k, kmask);
-                o1.y = d.two(rf, lut_s, k, kmask);
-                o1.z = d.two(rf, lut_s, k, kmask);
-                o1.w = d.two(rf, lut_s, k, kmask);
-                stg_256(optr, o0, o1);
+                stg_256(optr, make_uint4(o[0], o[1], o[2], o[3]), make_uint4(o[4], o[5], o[6], o[7]));
                 optr += 16;
-                if (pend_at == rf.fetched) {                 // (an on-demand top-up may have overtaken it)
-                    rf.store_chunk(rf.fetched, pend0);
-                    if (npend == 2) rf.store_chunk(rf.fetched + 4, pend1);
-                    rf.fetched += 4 * npend;
-                }
             }
         }
-        // ---- epilogue: the last < 8 samples --------------------------------------------------------
-        if (left) rf.ensure(d.wpos + 10u);
-        for (; left; --left) *optr++ = (int16_t)d.one(rf, lut_s, k, kmask);
+        // ---- epilogue: the last < 16 samples (the ring was topped up by the last pass) -------------
+        for (; left; --left) {
+            d.one(ring_b, k, kmask);
+            *optr++ = (int16_t)(d.S >> 16);
+        }
 
         // the codes must end inside the last word of the record
         if (n) {
-            const uint64_t used = (rf.base_al + d.wpos) - (rec + 1 + mis) + (d.bit ? 1u : 0u);
-            if (used != nwords) d.bad = true;
+            const uint32_t used_bits = d.bits() - start_bits;
+            if ((uint64_t)((used_bits + 31u) >> 5) != (uint64_t)nwords) d.bad = true;
         }
         if (d.bad) atomicOr(p.status, kErrStream);
     }
@@ -535,7 +543,7 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
     }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        cudaFuncSetAttribute(parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
         cudaFuncSetAttribute(parse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         attr_set = true;
     }
@@ -557,11 +565,13 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
         warps = (int)((ngroups + grid - 1) / grid);
         if (warps < 1) warps = 1;
     }
-    // shared layout: [pad to 2 KB] rings | table.  The dynamic area starts right after the 1 KB the
+    // shared layout: [pad to 32 KB] table | rings.  The dynamic area starts right after the 1 KB the
     // system reserves per CTA (the kernel checks the assumption).
     size_t off = 1024;
-    off = (off + kRingWords * 128 - 1) & ~(size_t)(kRingWords * 128 - 1);
-    off += (size_t)warps * kRingWords * 128 + (size_t)kLutSize * 4;
+    const size_t lut_at = (off + kLutBytes - 1) & ~(size_t)(kLutBytes - 1);
+    const size_t nbelow = (lut_at - off) / kRingBytes;
+    const size_t nabove = (size_t)warps > nbelow ? (size_t)warps - nbelow : 0;
+    off = lut_at + kLutBytes + nabove * kRingBytes;
     ParseParams pp = p;
     pp.smem_bytes = (uint32_t)(off - 1024);
     if (getenv("DRICE_DEBUG")) {
