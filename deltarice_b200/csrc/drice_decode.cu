@@ -9,10 +9,10 @@
 // Two kernels:
 //   locate_kernel  one CTA per chunk.  The stream has no index, only the chain
 //                  cur += word[cur] + 1 (:319-325); chasing it through HBM would cost one
-//                  DRAM round trip per wave, so the CTA streams the chunk through shared
-//                  memory (cp.async, double buffered) and one thread chases the chain at
-//                  shared-memory latency, writing the per-wave table (record position,
-//                  output position, sample count).  Tiles that hold no header are skipped.
+//                  DRAM round trip per wave, so one thread streams the chunk through shared
+//                  memory (bulk async copies on mbarriers, 128 KB in flight) and chases the
+//                  chain at shared-memory latency, writing the record positions; the other
+//                  warps fill the rest of the per-wave table (output position, sample count).
 //   parse_kernel   one THREAD per wave, 32 waves per warp: Rice parsing is a serial chain
 //                  per wave, so the parallelism is across waves.  Each lane streams its
 //                  record through a private shared-memory ring (128-bit loads issued one
@@ -28,192 +28,6 @@
 namespace drice {
 
 namespace {
-
-// ------------------------------------------------------------------------------------
-// locate
-// ------------------------------------------------------------------------------------
-// The stream has no index, only the chain cur += word[cur] + 1 (src/deltaRice.c:319-325), and a
-// hop through HBM costs a DRAM round trip.  One CTA per chunk therefore streams the chunk through
-// shared memory (cp.async, three tiles in flight) while ONE thread chases the chain at shared-
-// memory latency, writing the record positions of the tile to a list; the whole CTA then turns
-// the list into wave table entries.  Records longer than the pipeline are jumped over.
-constexpr int kLocThreads   = 256;
-constexpr int kLocTileWords = 8192;          // 32 KB per stage
-constexpr int kLocStages    = 3;
-constexpr int kLocListMax   = kLocTileWords;       // a record is at least its [nwords] word
-
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
-{
-    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// loads words [A, A+kLocTileWords) into `dst` ((comp + A) is 16-byte aligned; A may be negative
-// by up to 3 words when comp itself is not 16-byte aligned); words outside [0, limit) are skipped.
-__device__ __forceinline__ void locate_load_tile(uint32_t *dst, const uint32_t *comp, int64_t A, uint64_t limit)
-{
-    for (int v = threadIdx.x; v < kLocTileWords / 4; v += kLocThreads) {
-        const int64_t w = A + 4ll * v;
-        if (w >= 0 && (uint64_t)w + 4 <= limit) {
-            cp_async16(dst + 4 * v, comp + w);
-        } else {
-            for (int e = 0; e < 4; ++e)
-                if (w + e >= 0 && (uint64_t)(w + e) < limit) dst[4 * v + e] = comp[w + e];
-        }
-    }
-}
-
-__global__ void __launch_bounds__(kLocThreads) locate_kernel(const LocateParams p)
-{
-    extern __shared__ __align__(16) uint32_t stile[];   // kLocStages * kLocTileWords | list of kLocListMax
-    uint32_t *s_list = stile + kLocStages * kLocTileWords;      // tile-relative record positions
-    __shared__ uint64_t s_cur;
-    __shared__ uint32_t s_wave, s_cnt;
-    __shared__ int s_state;                              // 0 = next tile, 1 = done, 2 = jump to s_cur
-    const uint32_t c = blockIdx.x;
-    const uint64_t wb = p.chunk_word_off[c], we = p.chunk_word_off[c + 1];
-    const uint64_t sb = p.chunk_sample_off[c], se = p.chunk_sample_off[c + 1];
-    const uint32_t g0 = p.chunk_wave_off[c];
-    const uint32_t W = p.chunk_wave_off[c + 1] - g0;    // waves expected from the caller's sizes
-    const uint64_t total = se - sb;
-    const uint64_t Lw = p.L ? (uint64_t)p.L : total;
-
-    if (we <= wb) {                                      // no stream at all
-        if (threadIdx.x == 0) atomicOr(p.status, kErrStream);
-        return;
-    }
-    if (threadIdx.x == 0) {
-        if (p.comp[wb] != (uint32_t)total) atomicOr(p.status, kErrTotal);
-        if (W == 0 && we != wb + 1) atomicOr(p.status, kErrStream);
-        s_cur = wb + 1;
-        s_wave = 0;
-        s_state = (W == 0) ? 1 : 0;
-    }
-    __syncthreads();
-    if (s_state == 1) return;
-
-    // misalignment of the global address: tiles start at word indices A with (comp + A) 16-byte aligned
-    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(p.comp) >> 2) & 3u);
-    auto align_down = [mis](uint64_t w) { return (int64_t)((w + mis) & ~3ull) - (int64_t)mis; };
-
-    int64_t A = align_down(wb + 1);                      // first word of the oldest tile in flight
-    int head = 0;                                        // its stage
-    auto refill_all = [&]() {
-#pragma unroll
-        for (int sidx = 0; sidx < kLocStages; ++sidx) {
-            const int64_t At = A + (int64_t)sidx * kLocTileWords;
-            if ((uint64_t)(At < 0 ? 0 : At) < we) locate_load_tile(stile + ((head + sidx) % kLocStages) * kLocTileWords, p.comp, At, we);
-            cp_async_commit();
-        }
-    };
-    refill_all();
-    while (true) {
-        cp_async_wait<kLocStages - 1>();                 // the oldest tile has landed
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const uint32_t *t = stile + head * kLocTileWords;
-            uint64_t cur = s_cur;
-            uint32_t w = s_wave, cnt = 0;
-            const uint64_t tile_end = (uint64_t)(A + kLocTileWords);
-            const uint64_t stop = tile_end < we ? tile_end : we;
-            if (cur < stop) {
-                // tile-relative 32-bit chase: the dependent chain is one LDS + one add per hop
-                uint32_t rel = (uint32_t)((int64_t)cur - A);
-                const uint32_t stop_rel = (uint32_t)((int64_t)stop - A);
-                const uint32_t wleft = W - w;
-                while (cnt < wleft && rel < stop_rel) {
-                    s_list[cnt++] = rel;
-                    rel += t[rel] + 1u;
-                }
-                w += cnt;
-                cur = (uint64_t)(A + (int64_t)rel);
-            }
-            s_cur = cur;
-            s_cnt = cnt;
-            int state = 0;
-            if (w == W) {
-                if (cur != we) atomicOr(p.status, kErrStream);
-                state = 1;
-            } else if (cur >= we) {
-                atomicOr(p.status, kErrStream);
-                // neutralise the waves that could not be located
-                for (uint32_t x = w; x < W; ++x) { p.wave_in[g0 + x] = wb; p.wave_out[g0 + x] = sb; p.wave_n[g0 + x] = 0; }
-                state = 1;
-            } else if (cur >= (uint64_t)(A + (int64_t)kLocStages * kLocTileWords)) {
-                state = 2;                               // a record longer than everything in flight
-            }
-            s_state = state;
-        }
-        __syncthreads();
-        // the tile's records -> wave table, by everybody
-        {
-            const uint32_t cnt = s_cnt, w0 = s_wave;
-            for (uint32_t i = threadIdx.x; i < cnt; i += kLocThreads) {
-                const uint32_t w = w0 + i;
-                const uint64_t s0 = (uint64_t)w * Lw;
-                p.wave_in[g0 + w] = (uint64_t)(A + (int64_t)s_list[i]);
-                p.wave_out[g0 + w] = sb + s0;
-                p.wave_n[g0 + w] = (uint32_t)((total - s0) < Lw ? (total - s0) : Lw);
-            }
-        }
-        const int state = s_state;
-        __syncthreads();                                 // list and tile are free again
-        if (threadIdx.x == 0) s_wave += s_cnt;
-        if (state == 1) break;
-        if (state == 2) {                                // restart the pipeline at the record's header
-            cp_async_wait<0>();
-            __syncthreads();
-            A = align_down(s_cur);
-            head = 0;
-            refill_all();
-        } else {                                         // reuse the stage for the tile after the ones in flight
-            const int64_t An = A + (int64_t)kLocStages * kLocTileWords;
-            if ((uint64_t)An < we) locate_load_tile(stile + head * kLocTileWords, p.comp, An, we);
-            cp_async_commit();
-            A += kLocTileWords;
-            head = (head + 1) % kLocStages;
-        }
-    }
-    cp_async_wait<0>();
-}
-
-// ------------------------------------------------------------------------------------
-// parse
-// ------------------------------------------------------------------------------------
-// Rice parsing is a serial chain per wave (a code's length is only known once its unary
-// prefix has been read), so the parallelism is across waves: one LANE per wave, a warp takes
-// 32 consecutive waves per ticket.  The kernel is bound by issue slots and by the shared-memory
-// (MIO) pipe, so the inner loop is built around instructions and wavefronts per sample:
-//   * one code = one lookup: the next W stream bits index a shared-memory table built for the
-//     launch's k whose 4-byte entry is (delta << 16 | bits consumed).  The lane's whole decoder
-//     state is ONE register S = (running sample << 16 | bit position in its ring), so a code
-//     costs a single add: S += entry (the inverse delta and the bit pointer advance together;
-//     the low half is folded every 16 samples so that it never carries into the sample);
-//   * the table is replicated R times (entry index * R + lane % R): lanes that share a bank
-//     only conflict within their group of 32 / R lanes, which cuts the wavefronts per lookup
-//     from ~3.7 (random) to ~2 (R = 8, k = 2) - W and R are chosen per k to fill 32 KB;
-//   * four codes per window: a 64-bit window is rebuilt from three ring words addressed by the
-//     bit position (no window rotation, no per-sample refill test), then shifted by each code's
-//     length; the four results are checked for a miss ONCE (min of the entries == 0: escapes and
-//     codes longer than the window), in which case the group is redone code by code with
-//     count-leading-zeros;
-//   * every lane of the warp advances in lock step; 16 samples pack into one 32-byte sector that
-//     the lane stores straight to HBM - there is no shared-memory staging of the output;
-//   * the compressed words reach the lane through a private 32-word ring in shared memory
-//     ([word][lane], bank = lane: conflict free; rows 32/33 mirror rows 0/1 so that a window never
-//     wraps), refilled with one 32-byte load (a full sector) that is requested a block ahead.
-constexpr int      kRingWords  = 32;                 // compressed words per lane
-constexpr int      kRingRows   = kRingWords + 2;     // + mirror of rows 0 and 1
-constexpr uint32_t kRingBytes  = kRingRows * 128u;   // per warp
-constexpr int      kChunkWords = 8;                  // one 32-byte sector per refill
-constexpr uint32_t kLutBytes   = 32768;              // table incl. replication, aligned to its size
-constexpr int      kLutMaxBits = 12;
-constexpr uint32_t kAhead      = 16;                 // ring words guaranteed ahead at a block start:
-                                                     // 16 escapes (400 bits) + the 3-word window
-constexpr int kParseMaxWarps = 17;                   // per CTA; two CTAs per SM
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
@@ -239,6 +53,284 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v)
 {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+
+// ------------------------------------------------------------------------------------
+// locate
+// ------------------------------------------------------------------------------------
+// The stream has no index, only the chain cur += word[cur] + 1 (src/deltaRice.c:319-325), and a
+// hop through HBM costs a DRAM round trip.  One CTA per chunk therefore streams the chunk through
+// a 128 KB circular buffer in shared memory while ONE thread chases the chain at shared-memory
+// latency.  Three roles, no block barriers:
+//   producer  (warp 1, one thread) issues the tiles as bulk async copies (cp.async.bulk: one
+//             instruction per 32 KB tile, completion on the stage's `full` mbarrier) as soon as the
+//             chaser has released the stage (`empty` mbarrier);
+//   chaser    (warp 0, one thread) runs FOUR hops speculatively per iteration on byte offsets -
+//             the dependent chain is one multiply-add, one mask and one LDS per hop, everything
+//             else (the 64-bit record positions it stores, the bounds checks, handing tiles
+//             back) hides behind it; hops that ran past the loaded data are discarded;
+//   the other warps fill the part of the wave table that does not depend on the chain
+//             (output position, sample count).
+// Chunks whose waves are long (>= kLocDirectL samples: few, large records) are chased straight
+// through global memory instead - streaming them would move far more than the hops need.
+constexpr int      kLocThreads   = 128;
+constexpr int      kLocTileWords = 8192;          // 32 KB per stage
+constexpr int      kLocStages    = 4;
+constexpr uint32_t kLocRingWords = kLocTileWords * kLocStages;
+constexpr uint64_t kLocDirectL   = 32768;
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t mbar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
+{
+    while (!mbar_try_wait(mbar, parity)) { }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+// issues the tile of words [A, A + kLocTileWords) into the stage at shared address `dst`
+// ((comp + A) is 16-byte aligned; A may be negative by up to 3 words when comp itself is not):
+// the (at most 3 + 3) words around the 16-byte aligned part inside [0, limit) with plain loads,
+// then that part as one bulk copy that completes on `mbar`.
+__device__ __forceinline__ void locate_issue_tile(uint32_t dst, uint32_t mbar, const uint32_t *comp, int64_t A, uint64_t limit)
+{
+    const int64_t lo = A < 0 ? A + 4 : A;
+    int64_t hi = A + (int64_t)(((int64_t)limit - A) & ~3ll);          // same alignment class as A, <= limit
+    if (hi > A + kLocTileWords) hi = A + kLocTileWords;
+    if (hi < lo) hi = lo;
+    for (int64_t w = A < 0 ? 0 : A; w < lo && (uint64_t)w < limit; ++w) sts32(dst + (uint32_t)(w - A) * 4u, comp[w]);
+    for (int64_t w = hi; w < A + kLocTileWords && (uint64_t)w < limit; ++w) sts32(dst + (uint32_t)(w - A) * 4u, comp[w]);
+    const uint32_t bytes = (uint32_t)(hi - lo) * 4u;
+    if (bytes) {
+        mbar_arrive_expect_tx(mbar, bytes);
+        bulk_g2s(dst + (uint32_t)(lo - A) * 4u, comp + lo, bytes, mbar);
+    } else {
+        mbar_arrive(mbar);
+    }
+}
+
+__global__ void __launch_bounds__(kLocThreads) locate_kernel(const LocateParams p)
+{
+    extern __shared__ __align__(128) uint32_t stile[];  // the circular buffer: kLocStages tiles
+    __shared__ __align__(8) uint64_t s_full[kLocStages], s_empty[kLocStages];
+    __shared__ uint32_t s_located;                       // waves the chase reached
+    __shared__ volatile uint32_t s_done;                 // the chaser has finished (the producer may stop)
+    const uint32_t c = blockIdx.x;
+    const uint64_t wb = p.chunk_word_off[c], we = p.chunk_word_off[c + 1];
+    const uint64_t sb = p.chunk_sample_off[c], se = p.chunk_sample_off[c + 1];
+    const uint32_t g0 = p.chunk_wave_off[c];
+    const uint32_t W = p.chunk_wave_off[c + 1] - g0;    // waves expected from the caller's sizes
+    const uint64_t total = se - sb;
+    const uint64_t Lw = p.L ? (uint64_t)p.L : total;
+
+    if (we <= wb) {                                      // no stream at all
+        if (threadIdx.x == 0) atomicOr(p.status, kErrStream);
+        for (uint32_t w = threadIdx.x; w < W; w += kLocThreads) { p.wave_in[g0 + w] = wb; p.wave_out[g0 + w] = sb; p.wave_n[g0 + w] = 0; }
+        return;
+    }
+    if (W == 0) {
+        if (threadIdx.x == 0) {
+            if (p.comp[wb] != (uint32_t)total) atomicOr(p.status, kErrTotal);
+            if (we != wb + 1) atomicOr(p.status, kErrStream);
+        }
+        return;
+    }
+    const bool direct = Lw >= kLocDirectL || (we - wb) >= (1ull << 28);
+    const uint32_t stile_s = (uint32_t)__cvta_generic_to_shared(stile);
+    const uint32_t full_s = (uint32_t)__cvta_generic_to_shared(s_full);
+    const uint32_t empty_s = (uint32_t)__cvta_generic_to_shared(s_empty);
+    // misalignment of the global address: tiles start at word indices A with (comp + A) 16-byte aligned
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(p.comp) >> 2) & 3u);
+    const int64_t A0 = (int64_t)((wb + 1 + mis) & ~3ull) - (int64_t)mis;     // first word of tile 0
+    const uint32_t end_rel = (uint32_t)((int64_t)we - A0);                    // chunk end, words from A0
+    const uint32_t ntiles = (end_rel + kLocTileWords - 1) / kLocTileWords;
+    if (threadIdx.x == 0) {
+        s_done = 0;
+        s_located = W;
+        if (!direct) {
+#pragma unroll
+            for (int sidx = 0; sidx < kLocStages; ++sidx) {
+                mbar_init(full_s + 8u * sidx, 1u);
+                mbar_init(empty_s + 8u * sidx, 1u);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    __syncthreads();
+
+    if (threadIdx.x == 0 && direct) {
+        // ---- long waves: hop through global memory --------------------------------------------
+        if (p.comp[wb] != (uint32_t)total) atomicOr(p.status, kErrTotal);
+        uint64_t cur = wb + 1;
+        uint32_t w = 0;
+        while (w < W && cur < we) {
+            p.wave_in[g0 + w] = cur;
+            cur += (uint64_t)__ldg(p.comp + cur) + 1ull;
+            ++w;
+        }
+        if (w < W) s_located = w;
+        if (w < W || cur != we) atomicOr(p.status, kErrStream);
+    } else if (threadIdx.x == 0) {
+        // ---- chaser -----------------------------------------------------------------------------
+        // positions are BYTE offsets from tile 0 (32 bit: chunks of 1 GiB of stream and more go the
+        // direct way); a ring address is (offset & mask) + the buffer's (uniform) base
+        if (p.comp[wb] != (uint32_t)total) atomicOr(p.status, kErrTotal);
+        const char *ring = reinterpret_cast<const char *>(stile);
+        constexpr uint32_t kMask = kLocRingWords * 4u - 4u;
+        constexpr uint32_t kTileBytes = kLocTileWords * 4u;
+        const uint32_t end_b = end_rel * 4u;
+        uint32_t pos = (uint32_t)((int64_t)(wb + 1) - A0) * 4u;
+        uint32_t left = W;
+        uint64_t *wi = p.wave_in + g0;
+        uint32_t tiles_in = 1;                               // tiles waited for
+        uint32_t tiles_out = 0;                              // tiles released
+        mbar_wait(full_s, 0u);
+        uint32_t avail = end_b < kTileBytes ? end_b : kTileBytes;        // end of the loaded region
+        uint32_t rel_end = kTileBytes;                       // end of the oldest tile not yet released
+        auto hop = [ring](uint32_t o) {
+            uint32_t o4 = o + 4u;
+            asm volatile("" : "+r"(o4));                     // (keeps the + 4 off the dependent chain)
+            return o4 + 4u * *reinterpret_cast<const uint32_t *>(ring + (o & kMask));
+        };
+        auto record = [A0](uint32_t o) { return (uint64_t)(A0 + (int64_t)(o >> 2)); };
+        while (left && pos < end_b) {
+            if (pos >= rel_end) {                            // the chase has left the oldest tile: hand it back
+                mbar_arrive(empty_s + 8u * (tiles_out % kLocStages));
+                ++tiles_out;
+                rel_end += kTileBytes;
+                continue;
+            }
+            // four hops ahead; a hop beyond `avail` read stale data and is discarded
+            const uint32_t p1 = hop(pos);
+            const uint32_t p2 = hop(p1);
+            const uint32_t p3 = hop(p2);
+            const uint32_t p4 = hop(p3);
+            if (left >= 4u && p1 > pos && p1 < avail && p2 > p1 && p2 < avail && p3 > p2 && p3 < avail && p4 > p3) {
+                wi[0] = record(pos);
+                wi[1] = record(p1);
+                wi[2] = record(p2);
+                wi[3] = record(p3);
+                wi += 4;
+                left -= 4u;
+                pos = p4;
+            } else if (pos >= avail || (avail < end_b && left >= 4u)) {
+                // out of loaded data (or too close to its end for four hops): take the next tile in
+                mbar_wait(full_s + 8u * (tiles_in % kLocStages), (tiles_in / kLocStages) & 1u);
+                ++tiles_in;
+                const uint32_t te = tiles_in * kTileBytes;
+                avail = te < end_b ? te : end_b;
+            } else {
+                wi[0] = record(pos);
+                ++wi;
+                --left;
+                if (p1 <= pos) {                             // wrap: not a stream this path can hold
+                    pos = end_b + 4u;
+                    break;
+                }
+                pos = p1;
+            }
+        }
+        if (left) s_located = W - left;
+        if (left || pos != end_b) atomicOr(p.status, kErrStream);
+        s_done = 1;
+    } else if (threadIdx.x == 32 && !direct) {
+        // ---- producer ---------------------------------------------------------------------------
+        uint32_t issued = 0;
+        for (uint32_t t = 0; t < ntiles; ++t) {
+            const uint32_t sidx = t % kLocStages;
+            if (t >= (uint32_t)kLocStages) {
+                const uint32_t par = ((t / kLocStages) - 1u) & 1u;
+                bool stop = false;
+                while (!mbar_try_wait(empty_s + 8u * sidx, par)) {
+                    if (s_done) { stop = true; break; }
+                }
+                if (stop) break;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            locate_issue_tile(stile_s + sidx * (kLocTileWords * 4u), full_s + 8u * sidx, p.comp,
+                              A0 + (int64_t)t * kLocTileWords, p.comp_words);
+            issued = t + 1;
+        }
+        // nothing may still be landing in shared memory when the CTA exits: wait for the last tile
+        // issued into every stage
+        for (uint32_t sidx = 0; sidx < (uint32_t)kLocStages; ++sidx) {
+            if (issued > sidx) {
+                const uint32_t last = sidx + ((issued - 1u - sidx) / kLocStages) * kLocStages;   // last tile of this stage
+                mbar_wait(full_s + 8u * sidx, (last / kLocStages) & 1u);
+            }
+        }
+    } else if (threadIdx.x >= 64) {
+        // ---- the chain-independent part of the wave table -------------------------------------
+        for (uint32_t w = threadIdx.x - 64; w < W; w += kLocThreads - 64) {
+            const uint64_t s0 = (uint64_t)w * Lw;
+            p.wave_out[g0 + w] = sb + s0;
+            p.wave_n[g0 + w] = (uint32_t)((total - s0) < Lw ? (total - s0) : Lw);
+        }
+    }
+    __syncthreads();
+    // neutralise the waves that could not be located
+    for (uint32_t x = s_located + threadIdx.x; x < W; x += kLocThreads) { p.wave_in[g0 + x] = wb; p.wave_out[g0 + x] = sb; p.wave_n[g0 + x] = 0; }
+}
+
+// ------------------------------------------------------------------------------------
+// parse
+// ------------------------------------------------------------------------------------
+// Rice parsing is a serial chain per wave (a code's length is only known once its unary
+// prefix has been read), so the parallelism is across waves: one LANE per wave, a warp takes
+// 32 consecutive waves per ticket.  The kernel is bound by issue slots and by the shared-memory
+// (MIO) pipe, so the inner loop is built around instructions and wavefronts per sample:
+//   * one code = one lookup: the next W stream bits index a shared-memory table built for the
+//     launch's k whose 4-byte entry is (delta << 16 | bits consumed).  The lane's whole decoder
+//     state is ONE register S = (running sample << 16 | bit position in its ring), so a code
+//     costs a single add: S += entry (the inverse delta and the bit pointer advance together;
+//     the low half is folded every 16 samples so that it never carries into the sample);
+//   * the table is replicated R times (entry index * R + lane % R): lanes that share a bank
+//     only conflict within their group of 32 / R lanes, which cuts the wavefronts per lookup
+//     from ~3.7 (random) to ~2 (R = 8, k = 2) - W and R are chosen per k to fill 32 KB;
+//   * N codes per window (N * W <= 64: 6+5+5 per 16 samples for W <= 10, else 4x4): a 64-bit
+//     window is rebuilt from three ring words addressed by the bit position (no window rotation,
+//     no per-sample refill test), then shifted by each code's length; the N results are checked
+//     for a miss ONCE (min of the entries == 0: escapes and
+//     codes longer than the window), in which case the group is redone code by code with
+//     count-leading-zeros;
+//   * every lane of the warp advances in lock step; 16 samples pack into one 32-byte sector that
+//     the lane stores straight to HBM - there is no shared-memory staging of the output;
+//   * the compressed words reach the lane through a private 32-word ring in shared memory
+//     ([word][lane], bank = lane: conflict free; rows 32/33 mirror rows 0/1 so that a window never
+//     wraps), refilled with one 32-byte load (a full sector) that is requested a block ahead.
+constexpr int      kRingWords  = 32;                 // compressed words per lane
+constexpr int      kRingRows   = kRingWords + 2;     // + mirror of rows 0 and 1
+constexpr uint32_t kRingBytes  = kRingRows * 128u;   // per warp
+constexpr int      kChunkWords = 8;                  // one 32-byte sector per refill
+constexpr uint32_t kLutBytes   = 32768;              // table incl. replication, aligned to its size
+constexpr int      kLutMaxBits = 12;
+constexpr uint32_t kAhead      = 16;                 // ring words guaranteed ahead at a block start:
+                                                     // 16 escapes (400 bits) + the 3-word window
+constexpr int kParseMaxWarps = 17;                   // per CTA; two CTAs per SM
+
 struct Chunk8 { uint4 a, b; };
 // one full 32-byte sector, L2 only: every lane streams its own record
 __device__ __forceinline__ Chunk8 ldg_cg_256(const void *p)
@@ -347,6 +439,49 @@ struct LaneDec {
     __device__ __forceinline__ uint32_t bits() const { return tb + (S & 0xFFFFu); }   // from ring word 0
 };
 
+// N codes from one 64-bit window (N * W <= 64), samples FIRST .. FIRST+N-1 of a 16-sample block:
+// packs them (two per register) into o[]; `carry` holds the state after an odd sample that waits
+// for its partner in the next group
+template <int N, int FIRST>
+__device__ __forceinline__ void group(LaneDec &d, uint32_t ring_b, uint32_t lutl, uint32_t imask, uint32_t ish, int k,
+                                      uint32_t kmask, uint32_t (&o)[8], uint32_t &carry)
+{
+    const uint32_t S0 = d.S;
+    const uint32_t a = d.row_addr(ring_b);
+    const uint32_t w0 = lds32o<0>(a), w1 = lds32o<128>(a), w2 = lds32o<256>(a);
+    uint32_t hi = __funnelshift_l(w1, w0, S0);
+    uint32_t lo = __funnelshift_l(w2, w1, S0);
+    uint32_t st[N];
+    uint32_t S = S0, m = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const uint32_t e = lds32(((hi >> ish) & imask) | lutl);
+        S += e;
+        st[i] = S;
+        m = min(m, e);
+        if (i < N - 1) {
+            hi = __funnelshift_l(lo, hi, e);
+            if (i < N - 2) lo = __funnelshift_l(0u, lo, e);
+        }
+    }
+    d.S = S;
+    if (m == 0u) {                                           // an escape / a code longer than the window
+        d.S = S0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            d.one(ring_b, k, kmask);
+            st[i] = d.S;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const int smp = FIRST + i;
+        if (smp & 1) o[smp >> 1] = prmt(i ? st[i - 1] : carry, st[i], 0x7632);
+    }
+    if ((FIRST + N) & 1) carry = st[N - 1];
+}
+
+template <bool W10>
 __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const ParseParams p)
 {
     extern __shared__ __align__(16) uint32_t dsm[];
@@ -462,41 +597,18 @@ __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const Par
                 if (have_pend) pend = rf.load_chunk(rf.fetched);
             }
             if (b < nblk) {
+                // 16 samples as groups of N codes per window (N * W <= 64): 6+5+5 for W <= 10, else 4x4
                 uint32_t o[8];
-#pragma unroll
-                for (int gq = 0; gq < 4; ++gq) {
-                    const uint32_t S0 = d.S;
-                    const uint32_t a = d.row_addr(ring_b);
-                    const uint32_t w0 = lds32o<0>(a), w1 = lds32o<128>(a), w2 = lds32o<256>(a);
-                    uint32_t hi = __funnelshift_l(w1, w0, S0);
-                    uint32_t lo = __funnelshift_l(w2, w1, S0);
-                    const uint32_t e1 = lds32(((hi >> ish) & imask) | lutl);
-                    const uint32_t S1 = S0 + e1;
-                    hi = __funnelshift_l(lo, hi, e1);
-                    lo = __funnelshift_l(0u, lo, e1);
-                    const uint32_t e2 = lds32(((hi >> ish) & imask) | lutl);
-                    const uint32_t S2 = S1 + e2;
-                    hi = __funnelshift_l(lo, hi, e2);
-                    const uint32_t e3 = lds32(((hi >> ish) & imask) | lutl);
-                    const uint32_t S3 = S2 + e3;
-                    hi = __funnelshift_l(0u, hi, e3);
-                    const uint32_t e4 = lds32(((hi >> ish) & imask) | lutl);
-                    const uint32_t S4 = S3 + e4;
-                    uint32_t r01 = prmt(S1, S2, 0x7632), r23 = prmt(S3, S4, 0x7632);
-                    d.S = S4;
-                    if (min(min(e1, e2), min(e3, e4)) == 0u) {       // an escape / a code longer than the window
-                        d.S = S0;
-                        d.one(ring_b, k, kmask);
-                        const uint32_t t1 = d.S;
-                        d.one(ring_b, k, kmask);
-                        r01 = prmt(t1, d.S, 0x7632);
-                        d.one(ring_b, k, kmask);
-                        const uint32_t t3 = d.S;
-                        d.one(ring_b, k, kmask);
-                        r23 = prmt(t3, d.S, 0x7632);
-                    }
-                    o[2 * gq] = r01;
-                    o[2 * gq + 1] = r23;
+                uint32_t carry = 0;
+                if (W10) {
+                    group<6, 0>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
+                    group<5, 6>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
+                    group<5, 11>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
+                } else {
+                    group<4, 0>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
+                    group<4, 4>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
+                    group<4, 8>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
+                    group<4, 12>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
                 }
                 stg_256(optr, make_uint4(o[0], o[1], o[2], o[3]), make_uint4(o[4], o[5], o[6], o[7]));
                 optr += 16;
@@ -543,8 +655,10 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
     }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-        cudaFuncSetAttribute(parse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(parse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        cudaFuncSetAttribute(parse_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(parse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        cudaFuncSetAttribute(parse_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         attr_set = true;
     }
     const uint32_t ngroups = (p.nwaves + 31u) / 32u;
@@ -576,10 +690,13 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
     pp.smem_bytes = (uint32_t)(off - 1024);
     if (getenv("DRICE_DEBUG")) {
         int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, parse_kernel, warps * 32, pp.smem_bytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, parse_kernel<true>, warps * 32, pp.smem_bytes);
         fprintf(stderr, "parse: grid %u warps %d smem %u occ %d\n", grid, warps, pp.smem_bytes, occ);
     }
-    parse_kernel<<<grid, warps * 32, pp.smem_bytes, st>>>(pp);
+    if (lut_bits_for(p.k) <= 10)
+        parse_kernel<true><<<grid, warps * 32, pp.smem_bytes, st>>>(pp);
+    else
+        parse_kernel<false><<<grid, warps * 32, pp.smem_bytes, st>>>(pp);
     return 1;
 }
 
@@ -589,7 +706,7 @@ int launch_locate(const LocateParams &p, cudaStream_t st)
 {
     if (p.nchunks == 0) return 0;
     static bool attr_set = false;
-    const size_t smem = (size_t)(kLocStages * kLocTileWords + kLocListMax) * sizeof(uint32_t);
+    const size_t smem = (size_t)(kLocStages * kLocTileWords) * sizeof(uint32_t);
     if (!attr_set) {
         cudaFuncSetAttribute(locate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
