@@ -16,7 +16,9 @@ i.e. the harmonic combination of encode GB/s and decode GB/s, both also printed
 are larger than L2 (1.07 GB raw + 0.29 GB stream vs 126 MB), so no flush is needed.
 `e2e` = the same metric through the host-pointer C-ABI (drice_encode_batch_host /
 drice_decode_batch_host: what H5Z_filter_deltarice calls) with pinned HOST buffers, every
-step copying raw in + stream out, then stream in + raw out.
+step copying raw in + stream out and stream in + raw out.  Headline: two handles on two host
+threads, step s encodes while the streams of step s-1 are decoded (both PCIe directions busy);
+`e2e.sequential` = one handle, encode then decode.
 `--impl reference` times the UNMODIFIED reference (oracle/_ref/libref_omp.so, its own
 H5Z_filter_deltarice, OpenMP over all host cores) on a bounded sample of the same workload.
 """
@@ -350,32 +352,62 @@ def run_ours(args):
     assert int(d_status[0]) == 0
 
     # ---- e2e: host buffers through the chunk scheduler (what the H5Z callback calls) ----
+    # (a) sequential: encode the batch, then decode its streams (one handle, one direction of
+    #     PCIe busy at a time);
+    # (b) pipelined (the headline): two handles on two host threads - step s encodes the batch into
+    #     stream buffer s%2 while the streams step s-1 produced are decoded, so raw-in and raw-out
+    #     share the link's two directions.  Every step still encodes one batch and decodes one.
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     h_raw = codec.pinned_empty(x.numel(), np.int16)
     h_raw[:] = x.cpu().numpy()
-    h_comp = codec.pinned_empty(cap, np.uint8)
+    h_comp = [codec.pinned_empty(cap, np.uint8) for _ in range(2)]
     h_back = codec.pinned_empty(x.numel(), np.int16)
-    h_boff = np.zeros(nchunks + 1, dtype=np.uint64)
-    for _ in range(2):
-        nb = codec.encode_host_into(h_raw, off, M, L, h_comp, h_boff)
-        codec.decode_host_into(h_comp[:nb], h_boff, off, M, L, h_back)
+    h_boff = [np.zeros(nchunks + 1, dtype=np.uint64) for _ in range(2)]
+    for i in range(2):
+        nb = codec.encode_host_into(h_raw, off, M, L, h_comp[i], h_boff[i])
+        codec.decode_host_into(h_comp[i][:nb], h_boff[i], off, M, L, h_back)
     assert nb == comp_bytes and np.array_equal(h_back, h_raw)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        nb = codec.encode_host_into(h_raw, off, M, L, h_comp[0], h_boff[0])
+        codec.decode_host_into(h_comp[0][:nb], h_boff[0], off, M, L, h_back)
+    torch.cuda.synchronize()
+    t_e2e_seq = (time.perf_counter() - t0) * 1e3 / e2e_steps   # ms per step (wall: host work is part of it)
+
+    codec2 = d.DeltaRice(local_rank)
+    h_back[:] = 0
+
+    def _enc(i):
+        codec.encode_host_into(h_raw, off, M, L, h_comp[i], h_boff[i])
+
+    def _dec(i):
+        codec2.decode_host_into(h_comp[i][:comp_bytes], h_boff[i], off, M, L, h_back)
+
+    def _pipelined(nsteps):
+        for s_ in range(nsteps):
+            ta = threading.Thread(target=_enc, args=(s_ & 1,))
+            tb = threading.Thread(target=_dec, args=((s_ + 1) & 1,))
+            ta.start(); tb.start()
+            ta.join(); tb.join()
+
+    _pipelined(2)
     barrier()
     clocks.live(True)
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        nb = codec.encode_host_into(h_raw, off, M, L, h_comp, h_boff)
-        codec.decode_host_into(h_comp[:nb], h_boff, off, M, L, h_back)
+    _pipelined(e2e_steps)
     torch.cuda.synchronize()
-    t_e2e = (time.perf_counter() - t0) * 1e3 / e2e_steps       # ms per step (wall: host work is part of it)
+    t_e2e = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    assert np.array_equal(h_back, h_raw), "pipelined e2e: decode(encode(x)) != x"
+    codec2.close()
     clocks.live(False)
     clk = clocks.result()
 
     # ---- max over ranks ----
-    tt = torch.tensor([t_total, t_enc, t_dec, t_e2e], dtype=torch.float64, device=dev)
+    tt = torch.tensor([t_total, t_enc, t_dec, t_e2e, t_e2e_seq], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_total, t_enc, t_dec, t_e2e = [float(v) for v in tt.cpu()]
+    t_total, t_enc, t_dec, t_e2e, t_e2e_seq = [float(v) for v in tt.cpu()]
     ms_step = t_total / args.steps
     value = world * 2 * raw_bytes / (ms_step * 1e6)
     e2e_val = world * 2 * raw_bytes / (t_e2e * 1e6)
@@ -429,7 +461,10 @@ def run_ours(args):
             "ratio": round(ratio, 5),
             "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": raw_bytes + comp_bytes,
                     "d2h_bytes_per_step": comp_bytes + raw_bytes, "steps": e2e_steps, "ms_per_step": round(t_e2e, 2),
-                    "api": "drice_encode_batch_host + drice_decode_batch_host (pinned host buffers)"},
+                    "api": "drice_encode_batch_host + drice_decode_batch_host (pinned host buffers), two handles: "
+                           "step s encodes while the streams of step s-1 are decoded (both PCIe directions busy)",
+                    "sequential": {"value": round(world * 2 * raw_bytes / (t_e2e_seq * 1e6), 2), "ms_per_step": round(t_e2e_seq, 2),
+                                   "api": "one handle: encode the batch, then decode its streams"}},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
