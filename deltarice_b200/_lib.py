@@ -24,14 +24,14 @@ class DeltaRiceError(RuntimeError):
 
 
 class Params(C.Structure):
-    _fields_ = [("M", C.c_int32), ("L", C.c_int32), ("filter_len", C.c_int32), ("filter", C.c_int32 * 8)]
+    _fields_ = [("M", C.c_int32), ("L", C.c_int32), ("filter_len", C.c_int32), ("filter", C.c_int32 * 16)]
 
 
 # every symbol include/deltarice_b200.h and include/deltaRice.h declare
 C_ABI_SYMBOLS = [
     "drice_abi_version", "drice_log2_param", "drice_parse_cd_values", "drice_chunk_bound_bytes",
     "drice_batch_bound_bytes", "drice_create", "drice_destroy", "drice_last_error", "drice_device",
-    "drice_host_alloc", "drice_host_free", "drice_encode_batch_dev_async", "drice_encode_batch_dev",
+    "drice_set_filter", "drice_host_alloc", "drice_host_free", "drice_encode_batch_dev_async", "drice_encode_batch_dev",
     "drice_decode_batch_dev_async", "drice_decode_batch_dev", "drice_encode_batch_host",
     "drice_decode_batch_host", "drice_peek_chunk_samples", "drice_launch_count",
     "drice_timing_enable", "drice_timing_read", "drice_kernel_name",
@@ -69,6 +69,8 @@ def load() -> C.CDLL:
     L.drice_last_error.argtypes = [vp]
     L.drice_device.restype = i
     L.drice_device.argtypes = [vp]
+    L.drice_set_filter.restype = i
+    L.drice_set_filter.argtypes = [vp, C.POINTER(C.c_int32), i]
     L.drice_host_alloc.restype = vp
     L.drice_host_alloc.argtypes = [sz]
     L.drice_host_free.restype = None

@@ -47,6 +47,18 @@ def chunk_offsets(chunk_samples: int | Sequence[int], total: int | None = None) 
     return np.concatenate([np.zeros(1, np.uint64), np.cumsum(cs, dtype=np.uint64)])
 
 
+def parse_cd_values_full(cd_values: Sequence[int] = ()) -> tuple[int, int, tuple]:
+    """compression_opts -> (M, L, filter taps) exactly as the filter callback parses them
+    (reference parseCD_VALUES, src/deltaRice.c:248-291)."""
+    L = _lib.load()
+    prm = _lib.Params()
+    cd = (C.c_uint * max(1, len(cd_values)))(*[int(v) & 0xFFFFFFFF for v in cd_values])
+    rc = L.drice_parse_cd_values(len(cd_values), cd, C.byref(prm))
+    if rc != 0:
+        raise DeltaRiceError(rc, f"bad compression_opts {tuple(cd_values)}")
+    return int(prm.M), int(prm.L), tuple(int(prm.filter[i]) for i in range(prm.filter_len))
+
+
 def parse_cd_values(cd_values: Sequence[int] = ()) -> tuple[int, int]:
     """compression_opts -> (M, L) exactly as the filter callback parses them."""
     L = _lib.load()
@@ -98,6 +110,17 @@ class DeltaRice:
     def _check(self, rc: int):
         if rc != 0:
             raise DeltaRiceError(rc, (self._L.drice_last_error(self._h) or b"").decode())
+
+    def set_filter(self, taps=None):
+        """Pre-filter of the following encode / decode calls (reference cd_values[3:]): None = the
+        delta filter [1,-1] (fused in the kernels), (1,) = none, anything else = FIR before encode /
+        recursion + division by taps[0] after decode (reference src/deltaRice.c:64-74, :91-102)."""
+        if taps is None:
+            self._check(self._L.drice_set_filter(self._h, None, 0))
+        else:
+            t = [int(v) for v in taps]
+            arr = (C.c_int32 * max(1, len(t)))(*t)
+            self._check(self._L.drice_set_filter(self._h, arr, len(t)))
 
     @property
     def launches(self) -> int:

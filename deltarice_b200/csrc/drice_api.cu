@@ -58,6 +58,11 @@ struct drice_ctx {
     cudaStream_t s_in = nullptr, s_out = nullptr;   // the device's shared copy streams (not owned)
     std::string err;
     uint64_t launches = 0;
+    // pre-filter of the next calls (drice_set_filter): 0 = delta [1,-1] (fused), 1 = none ([1]), 2 = generic taps
+    int filter_mode = 0;
+    int filter_len = 2;
+    int filter[drice::kMaxFilter] = {1, -1};
+    DevBuf d_filt;                       // generic filter: pre-filtered samples of the batch
 
     // optional per-kernel timing (drice_timing_*): event pairs recorded around launches
     bool timing = false;
@@ -272,11 +277,10 @@ extern "C" int drice_parse_cd_values(size_t n, const unsigned int *cd, drice_par
     if (n >= 3) {
         out->filter_len = (int32_t)cd[2];
         if (out->filter_len <= 0 || (size_t)out->filter_len + 3 > n) return DRICE_E_PARAM;
-        if (out->filter_len > 8) return DRICE_E_UNSUPPORTED;
+        if (out->filter_len > DRICE_MAX_FILTER) return DRICE_E_UNSUPPORTED;
         for (int f = 0; f < out->filter_len; ++f) out->filter[f] = (int32_t)cd[3 + f];
-        // only the delta filter [1,-1] is on the GPU path; anything else is refused rather
-        // than mis-encoded (no CPU fallback)
-        if (!(out->filter_len == 2 && out->filter[0] == 1 && out->filter[1] == -1)) return DRICE_E_UNSUPPORTED;
+        // decode divides by f[0] (src/deltaRice.c:100): the reference would trap (Appendix B9)
+        if (out->filter[0] == 0) return DRICE_E_PARAM;
     }
     if (drice_log2_param(out->M) < 0) return DRICE_E_PARAM;
     if (out->L == 0 || out->L < -1) return DRICE_E_PARAM;
@@ -376,7 +380,7 @@ extern "C" void drice_destroy(drice_ctx *ctx)
     }
     for (auto &t : ctx->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
-    ctx->d_tab.release(); ctx->d_scratch.release(); ctx->d_offs.release();
+    ctx->d_tab.release(); ctx->d_scratch.release(); ctx->d_offs.release(); ctx->d_filt.release();
     if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
     if (ctx->h_sync) cudaFreeHost(ctx->h_sync);
     if (ctx->ev_tab) cudaEventDestroy(ctx->ev_tab);
@@ -386,6 +390,26 @@ extern "C" void drice_destroy(drice_ctx *ctx)
 
 extern "C" const char *drice_last_error(const drice_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 extern "C" int drice_device(const drice_ctx *ctx) { return ctx ? ctx->device : -1; }
+extern "C" int drice_set_filter(drice_ctx *ctx, const int32_t *filter, int filter_len)
+{
+    if (!ctx) return DRICE_E_PARAM;
+    if (!filter) {                                       // back to the default delta filter
+        ctx->filter_mode = 0;
+        ctx->filter_len = 2;
+        ctx->filter[0] = 1;
+        ctx->filter[1] = -1;
+        return DRICE_OK;
+    }
+    if (filter_len < 1) return fail(ctx, DRICE_E_PARAM, "empty pre-filter");
+    if (filter_len > DRICE_MAX_FILTER) return fail(ctx, DRICE_E_UNSUPPORTED, "pre-filter longer than DRICE_MAX_FILTER taps");
+    if (filter[0] == 0) return fail(ctx, DRICE_E_PARAM, "pre-filter tap 0 must not be 0 (decode divides by it)");
+    ctx->filter_len = filter_len;
+    for (int i = 0; i < filter_len; ++i) ctx->filter[i] = filter[i];
+    // src/deltaRice.c:38-46 (checkIfDeltaFilter); [1] is the identity: nothing to run
+    ctx->filter_mode = (filter_len == 2 && filter[0] == 1 && filter[1] == -1) ? 0 : (filter_len == 1 && filter[0] == 1) ? 1 : 2;
+    return DRICE_OK;
+}
+
 extern "C" uint64_t drice_launch_count(const drice_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int drice_timing_enable(drice_ctx *ctx, int on)
@@ -467,8 +491,27 @@ extern "C" int drice_encode_batch_dev_async(drice_ctx *ctx, const int16_t *d_raw
     DR_CUDA(ctx, ctx->d_scratch.reserve(scratch));
     DR_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch.p, 0, zeroed, st));
 
+    const int16_t *src = d_raw;
+    if (ctx->filter_mode == 2) {
+        // generic pre-filter (src/deltaRice.c:64-74): raw -> scratch, then coded with the delta off
+        const size_t fb = (size_t)off[nchunks] * 2 + 64;
+        if (fb > ctx->d_filt.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
+        DR_CUDA(ctx, ctx->d_filt.reserve(fb));
+        FilterParams fp{};
+        fp.chunk_sample_off = d_soff;
+        fp.nchunks = (uint32_t)nchunks;
+        fp.L = g.Lk;
+        fp.flen = ctx->filter_len;
+        for (int i = 0; i < ctx->filter_len; ++i) fp.f[i] = ctx->filter[i];
+        uint64_t max_chunk = 0;
+        for (size_t c = 0; c < nchunks; ++c) max_chunk = std::max<uint64_t>(max_chunk, off[c + 1] - off[c]);
+        ctx->launches += (uint64_t)launch_prefilter(fp, d_raw, (int16_t *)ctx->d_filt.p, max_chunk, st);
+        src = (const int16_t *)ctx->d_filt.p;
+    }
     EncodeParams p{};
-    p.raw = d_raw;
+    p.raw = src;
+    p.mul_x = ctx->filter_mode == 0 ? 0xFFFF0001u : 1u;
+    p.neg_prev = ctx->filter_mode == 0 ? 0xFFFFFFFFu : 0u;
     p.raw_samples = off[nchunks];
     p.out = d_out;
     p.out_cap_words = out_cap_bytes / 4;
@@ -598,6 +641,7 @@ extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_co
     pp.nwaves = g.nwaves;
     pp.max_n = g.max_wave;
     pp.k = k;
+    pp.identity = ctx->filter_mode != 0;
     // widest store that every wave start allows
     int store_bytes = (int)(g.align_samples * 2);
     while (store_bytes > 2 && (reinterpret_cast<uintptr_t>(d_out) & (uintptr_t)(store_bytes - 1))) store_bytes >>= 1;
@@ -609,6 +653,18 @@ extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_co
     }
     if (nl < 0) return fail(ctx, DRICE_E_PARAM, "unsupported RiceParameter");
     ctx->launches += (uint64_t)nl;
+    if (ctx->filter_mode == 2) {
+        // inverse of the generic pre-filter (src/deltaRice.c:91-102), in place on the output
+        FilterParams fp{};
+        fp.chunk_sample_off = d_soff;
+        fp.nchunks = (uint32_t)nchunks;
+        fp.L = g.Lk;
+        fp.flen = ctx->filter_len;
+        for (int i = 0; i < ctx->filter_len; ++i) fp.f[i] = ctx->filter[i];
+        uint64_t max_waves = 0;
+        for (size_t c = 0; c < nchunks; ++c) max_waves = std::max<uint64_t>(max_waves, g.wave_off[c + 1] - g.wave_off[c]);
+        ctx->launches += (uint64_t)launch_postfilter(fp, d_out, max_waves, st);
+    }
     DR_CUDA(ctx, cudaGetLastError());
     return DRICE_OK;
 }

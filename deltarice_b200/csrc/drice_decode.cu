@@ -442,7 +442,7 @@ struct LaneDec {
 // N codes from one 64-bit window (N * W <= 64), samples FIRST .. FIRST+N-1 of a 16-sample block:
 // packs them (two per register) into o[]; `carry` holds the state after an odd sample that waits
 // for its partner in the next group
-template <int N, int FIRST>
+template <int N, int FIRST, bool IDENT>
 __device__ __forceinline__ void group(LaneDec &d, uint32_t ring_b, uint32_t lutl, uint32_t imask, uint32_t ish, int k,
                                       uint32_t kmask, uint32_t (&o)[8], uint32_t &carry)
 {
@@ -473,6 +473,11 @@ __device__ __forceinline__ void group(LaneDec &d, uint32_t ring_b, uint32_t lutl
             st[i] = d.S;
         }
     }
+    if (IDENT) {
+        // no inverse delta: the sample is the decoded value itself = the step of the running state
+#pragma unroll
+        for (int i = N - 1; i >= 0; --i) st[i] -= i ? st[i - 1] : S0;
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const int smp = FIRST + i;
@@ -481,7 +486,7 @@ __device__ __forceinline__ void group(LaneDec &d, uint32_t ring_b, uint32_t lutl
     if ((FIRST + N) & 1) carry = st[N - 1];
 }
 
-template <bool W10>
+template <bool W10, bool IDENT>
 __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const ParseParams p)
 {
     extern __shared__ __align__(16) uint32_t dsm[];
@@ -569,8 +574,9 @@ __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const Par
             if (pro > left) pro = left;
             left -= pro;
             for (; pro; --pro) {
+                const uint32_t Sb = d.S;
                 d.one(ring_b, k, kmask);
-                *optr++ = (int16_t)(d.S >> 16);
+                *optr++ = (int16_t)((IDENT ? d.S - Sb : d.S) >> 16);
             }
         }
         // ---- blocks of 16 samples: 4 groups of four codes, one 32-byte store (a full sector) -------
@@ -601,14 +607,14 @@ __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const Par
                 uint32_t o[8];
                 uint32_t carry = 0;
                 if (W10) {
-                    group<6, 0>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
-                    group<5, 6>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
-                    group<5, 11>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
+                    group<6, 0, IDENT>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
+                    group<5, 6, IDENT>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
+                    group<5, 11, IDENT>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
                 } else {
-                    group<4, 0>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
-                    group<4, 4>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
-                    group<4, 8>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
-                    group<4, 12>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
+                    group<4, 0, IDENT>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
+                    group<4, 4, IDENT>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
+                    group<4, 8, IDENT>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
+                    group<4, 12, IDENT>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
                 }
                 stg_256(optr, make_uint4(o[0], o[1], o[2], o[3]), make_uint4(o[4], o[5], o[6], o[7]));
                 optr += 16;
@@ -616,8 +622,9 @@ __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const Par
         }
         // ---- epilogue: the last < 16 samples (the ring was topped up by the last pass) -------------
         for (; left; --left) {
+            const uint32_t Sb = d.S;
             d.one(ring_b, k, kmask);
-            *optr++ = (int16_t)(d.S >> 16);
+            *optr++ = (int16_t)((IDENT ? d.S - Sb : d.S) >> 16);
         }
 
         // the codes must end inside the last word of the record
@@ -655,10 +662,14 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
     }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(parse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-        cudaFuncSetAttribute(parse_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(parse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-        cudaFuncSetAttribute(parse_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(parse_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        cudaFuncSetAttribute(parse_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(parse_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        cudaFuncSetAttribute(parse_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(parse_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        cudaFuncSetAttribute(parse_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(parse_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        cudaFuncSetAttribute(parse_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         attr_set = true;
     }
     const uint32_t ngroups = (p.nwaves + 31u) / 32u;
@@ -690,13 +701,17 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
     pp.smem_bytes = (uint32_t)(off - 1024);
     if (getenv("DRICE_DEBUG")) {
         int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, parse_kernel<true>, warps * 32, pp.smem_bytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, parse_kernel<true, false>, warps * 32, pp.smem_bytes);
         fprintf(stderr, "parse: grid %u warps %d smem %u occ %d\n", grid, warps, pp.smem_bytes, occ);
     }
-    if (lut_bits_for(p.k) <= 10)
-        parse_kernel<true><<<grid, warps * 32, pp.smem_bytes, st>>>(pp);
-    else
-        parse_kernel<false><<<grid, warps * 32, pp.smem_bytes, st>>>(pp);
+    const bool w10 = lut_bits_for(p.k) <= 10;
+    if (p.identity) {
+        if (w10) parse_kernel<true, true><<<grid, warps * 32, pp.smem_bytes, st>>>(pp);
+        else     parse_kernel<false, true><<<grid, warps * 32, pp.smem_bytes, st>>>(pp);
+    } else {
+        if (w10) parse_kernel<true, false><<<grid, warps * 32, pp.smem_bytes, st>>>(pp);
+        else     parse_kernel<false, false><<<grid, warps * 32, pp.smem_bytes, st>>>(pp);
+    }
     return 1;
 }
 

@@ -292,20 +292,22 @@ struct SweepState {
 
 // One round = 512 samples = 16 per lane.  kFull: every lane holds 16 valid samples.
 template <int K, bool kDirect, bool kFull>
-__device__ __forceinline__ void encode_round(RawWords &cur, uint32_t nvalid, bool last_lane, int lane,
+__device__ __forceinline__ void encode_round(const EncodeParams &p, RawWords &cur, uint32_t nvalid, bool last_lane, int lane,
                                              uint32_t *dst, uint32_t cap, SweepState &st)
-{
+{   // p.mul_x / p.neg_prev (read straight from the parameter bank): the pre-filter mode
     using C = RiceConst<K>;
     constexpr bool kPairs = C::kPairs;
     constexpr uint32_t M = C::M;
     uint32_t (&w)[8] = cur.w;
     // short last slot: repeat the last valid sample; its codes (delta 0) trail the lane's bits
     // and are cut off below
+    // (no pre-filter: the padding samples are zero instead, which codes the same K+1 bits)
     if (!kFull && nvalid > 0 && nvalid < (uint32_t)S) {
+        const uint32_t sel_hi = p.neg_prev ? 0x1010u : 0x4410u, sel_all = p.neg_prev ? 0x3232u : 0x4444u;
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
-            if (2u * v + 1 == nvalid) w[v] = prmt(w[v], 0, 0x1010);
-            if (v > 0 && 2u * v >= nvalid) w[v] = prmt(w[v - 1], 0, 0x3232);
+            if (2u * v + 1 == nvalid) w[v] = prmt(w[v], 0, sel_hi);
+            if (v > 0 && 2u * v >= nvalid) w[v] = prmt(w[v - 1], 0, sel_all);
         }
     }
     // word holding the sample before this lane's first one in its HIGH half
@@ -320,8 +322,8 @@ __device__ __forceinline__ void encode_round(RawWords &cur, uint32_t nvalid, boo
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
         const uint32_t prev = m ? w[m - 1] : pw;
-        const uint32_t X = w[m] * 0xFFFF0001u;              // high half: hi(w) - lo(w)
-        const uint32_t Y = w[m] - (prev >> 16);             // low half:  lo(w) - hi(prev)
+        const uint32_t X = w[m] * p.mul_x;                  // high half: hi(w) - lo(w)   [no delta: hi(w)]
+        const uint32_t Y = mad_lo(prev >> 16, p.neg_prev, w[m]);   // low half: lo(w) - hi(prev)   [no delta: lo(w)]
         const uint32_t D = prmt(Y, X, 0x7610);
         const uint32_t Sg = prmt(D, 0, 0xbb99);             // per-half sign mask
         U[m] = __vadd2(D, D) ^ Sg;
@@ -452,7 +454,7 @@ __device__ __forceinline__ void encode_round(RawWords &cur, uint32_t nvalid, boo
 // kDirect = true: packs straight into the record in HBM, `cap` = the wave's word count (nothing
 // is stored past it).  Returns the wave's bit count.
 template <int K, bool kDirect>
-__device__ __forceinline__ uint32_t encode_wave(const int16_t *wave, uint32_t n, const int16_t *raw_hi, int lane,
+__device__ __forceinline__ uint32_t encode_wave(const EncodeParams &p, const int16_t *wave, uint32_t n, const int16_t *raw_hi, int lane,
                                                 uint32_t *dst, uint32_t cap, bool *overflow)
 {
     const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(wave) & 15u) >> 1);
@@ -479,9 +481,9 @@ __device__ __forceinline__ uint32_t encode_wave(const int16_t *wave, uint32_t n,
         RawWords now = cur;
         q += kRound;
         if (r + 1 < nfull) load_slot(cur, q, mis); else load_slot_tail(cur, wave + tail_s0, mis, tail_valid, raw_hi);
-        encode_round<K, kDirect, true>(now, S, false, lane, dst, cap, st);
+        encode_round<K, kDirect, true>(p, now, S, false, lane, dst, cap, st);
     }
-    encode_round<K, kDirect, false>(cur, tail_valid, tail_valid > 0 && tail_s0 + S >= n, lane, dst, cap, st);
+    encode_round<K, kDirect, false>(p, cur, tail_valid, tail_valid > 0 && tail_s0 + S >= n, lane, dst, cap, st);
     __syncwarp();
     *overflow = st.ovf;
     return st.base;
@@ -562,7 +564,7 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
                 have = true;
                 wg = locate_wave(p, g);
                 if (wg.chunk_total) {
-                    nwords = (encode_wave<K, false>(p.raw + wg.begin, wg.n, raw_hi, lane, stage0 + par * stage_words,
+                    nwords = (encode_wave<K, false>(p, p.raw + wg.begin, wg.n, raw_hi, lane, stage0 + par * stage_words,
                                                     stage_words, &ovf) + 31u) >> 5;
                     mine = nwords + 1u;
                 }
@@ -617,7 +619,7 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
                         for (uint32_t i = lane; i < nwords_prev; i += 32) rec[1 + i] = src[i];
                     } else {                                 // larger than the staging: pack in place
                         bool dummy;
-                        encode_wave<K, true>(p.raw + wg_prev.begin, wg_prev.n, raw_hi, lane, rec + 1, nwords_prev, &dummy);
+                        encode_wave<K, true>(p, p.raw + wg_prev.begin, wg_prev.n, raw_hi, lane, rec + 1, nwords_prev, &dummy);
                     }
                 }
             }
@@ -666,8 +668,8 @@ __device__ __forceinline__ uint32_t rice_code_packed(uint32_t u)
 // aligned to memory (32 bytes), not to the wave.
 template <int K>
 __device__ __forceinline__ uint32_t slot_codes(const int16_t *wave, int64_t s0, uint32_t n,
-                                               uint32_t (&cv)[kSamplesPerThread])
-{
+                                               uint32_t (&cv)[kSamplesPerThread], int dmask)
+{   // dmask: -1 = delta pre-filter, 0 = none (the samples are coded as they are)
     const int64_t lo64 = -s0, hi64 = (int64_t)n - s0;
     const int jlo = lo64 > 0 ? (int)(lo64 < S ? lo64 : S) : 0;
     const int jhi = hi64 < S ? (int)(hi64 > 0 ? hi64 : 0) : S;
@@ -691,7 +693,7 @@ __device__ __forceinline__ uint32_t slot_codes(const int16_t *wave, int64_t s0, 
         }
 #pragma unroll
         for (int j = 0; j < S; ++j) {
-            cv[j] = rice_code_packed<K>(zigzag_delta(x[j + 1], x[j]));
+            cv[j] = rice_code_packed<K>(zigzag_delta(x[j + 1], x[j] & dmask));
             T += cv[j] >> 24;
         }
     } else {
@@ -700,7 +702,7 @@ __device__ __forceinline__ uint32_t slot_codes(const int16_t *wave, int64_t s0, 
         for (int j = 0; j < S; ++j) x[j + 1] = (j >= jlo && j < jhi) ? (int)sp[j] : 0;
 #pragma unroll
         for (int j = 0; j < S; ++j) {
-            const uint32_t c = rice_code_packed<K>(zigzag_delta(x[j + 1], x[j]));
+            const uint32_t c = rice_code_packed<K>(zigzag_delta(x[j + 1], x[j] & dmask));
             cv[j] = (j >= jlo && j < jhi) ? c : 0u;
             T += cv[j] >> 24;
         }
@@ -774,7 +776,7 @@ __device__ __forceinline__ void pack_slot(const uint32_t (&cv)[kSamplesPerThread
 // packing sweep of one wave by a whole CTA: codes are recomputed tile by tile, packed in
 // shared memory and completed words streamed to rec[1..]
 template <int K>
-__device__ __forceinline__ void pack_wave_streaming(const int16_t *wave, uint32_t n, uint32_t *rec, uint32_t *smem)
+__device__ __forceinline__ void pack_wave_streaming(const int16_t *wave, uint32_t n, uint32_t *rec, uint32_t *smem, int dmask)
 {
     const int NT = blockDim.x;
     const int tid = threadIdx.x;
@@ -791,7 +793,7 @@ __device__ __forceinline__ void pack_wave_streaming(const int16_t *wave, uint32_
     __syncthreads();
     uint64_t P = 0;                            // bits emitted so far
     for (uint32_t t = 0; t < ntiles; ++t) {
-        const uint32_t T = slot_codes<K>(wave, ((int64_t)t * NT + tid) * S - mis, n, cv);
+        const uint32_t T = slot_codes<K>(wave, ((int64_t)t * NT + tid) * S - mis, n, cv, dmask);
         uint32_t total;
         const uint32_t boff = block_excl_scan(T, swarp, &total);
         const uint32_t pre = (uint32_t)(P & 31u);          // bits already in word 0 (carry)
@@ -848,7 +850,7 @@ encode_multi_kernel(const EncodeParams p)
     // ---- sizing sweep ----------------------------------------------------------------
     uint64_t bits = 0;
     for (uint32_t t = 0; t < ntiles; ++t)
-        bits += slot_codes<K>(wave, ((int64_t)t * NT + tid) * S - mis, wg.n, cv);
+        bits += slot_codes<K>(wave, ((int64_t)t * NT + tid) * S - mis, wg.n, cv, (int)p.neg_prev);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
     uint64_t *s64 = reinterpret_cast<uint64_t *>(smem);
@@ -881,7 +883,7 @@ encode_multi_kernel(const EncodeParams p)
         if (rec_words) rec[0] = nwords;
     }
     if (rec_words == 0) return;
-    pack_wave_streaming<K>(wave, wg.n, rec, smem);
+    pack_wave_streaming<K>(wave, wg.n, rec, smem, (int)p.neg_prev);
 }
 
 int g_num_sms = 0;

@@ -42,6 +42,19 @@ struct EncodeParams {
     uint32_t        uniform_wpc;        // >0: every chunk has exactly this many waves
     uint32_t        L;                  // 0 = whole chunk is one wave
     int             k;
+    // pre-filter mode: delta (src/deltaRice.c:53-62) = (0xFFFF0001, 0xFFFFFFFF); none = (1, 0):
+    // the samples are Rice-coded as they are (filter [1], or already filtered by prefilter_kernel)
+    uint32_t        mul_x, neg_prev;
+};
+
+// generic pre-filter (src/deltaRice.c:64-74 / :91-102), taps by value
+constexpr int kMaxFilter = 16;
+struct FilterParams {
+    const uint64_t *chunk_sample_off;   // [nchunks+1] (device)
+    uint32_t        nchunks;
+    uint32_t        L;                  // 0 = whole chunk is one wave
+    int             flen;
+    int             f[kMaxFilter];
 };
 
 struct LocateParams {
@@ -71,11 +84,16 @@ struct ParseParams {
     uint32_t        max_n;              // longest wave in the batch
     uint32_t        smem_bytes;         // dynamic shared memory of the launch (set by the launcher)
     int             k;
+    int             identity;           // 1: write the decoded values themselves (no inverse delta)
 };
 
 // launchers (drice_encode.cu / drice_decode.cu); return launches enqueued
 int launch_encode(const EncodeParams &p, uint32_t max_wave_len, cudaStream_t st);
 int launch_locate(const LocateParams &p, cudaStream_t st);
 int launch_parse(const ParseParams &p, int store_bytes, cudaStream_t st);
+// out[i] = sum_j in[i-j] * f[j] per wave (mod 2^16); in != out
+int launch_prefilter(const FilterParams &p, const int16_t *in, int16_t *out, uint64_t max_chunk_samples, cudaStream_t st);
+// in place: y[i] = (d[i] - sum_{j>=1} y[i-j] * f[j]) / f[0] per wave
+int launch_postfilter(const FilterParams &p, int16_t *data, uint64_t nwaves_hint, cudaStream_t st);
 
 }  // namespace drice

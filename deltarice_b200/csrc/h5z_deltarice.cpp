@@ -15,7 +15,7 @@
 //   B1  H5PLget_plugin_info returns the class pointer (reference returns (void*)32025)
 //   B2  failure returns 0 (reference returns (size_t)-1) and leaves *buf untouched
 //   B5/B9/B10  invalid M, WaveformLength 0, odd byte counts, empty filters are rejected
-//   generic pre-filters (cd_nelmts >= 3 other than [1,-1]) are refused, not mis-encoded
+//   generic pre-filters (cd_nelmts >= 3): up to 16 taps, first tap != 0 (the reference divides by it)
 #include "../../include/deltaRice.h"
 #include "../../include/deltarice_b200.h"
 #ifdef DRICE_USE_SYSTEM_HDF5
@@ -69,13 +69,20 @@ size_t H5Z_filter_deltarice(unsigned flags, size_t cd_nelmts, const unsigned cd_
     const int prc = drice_parse_cd_values(cd_nelmts, cd_values, &prm);
     if (prc != DRICE_OK) {
         fprintf(stderr, prc == DRICE_E_UNSUPPORTED
-                            ? "deltarice_b200: only the delta pre-filter [1,-1] is implemented on the GPU path\n"
-                            : "deltarice_b200: invalid compression_opts (RiceParameter must be 2^k <= 32768, WaveformLength >= 1 or -1)\n");
+                            ? "deltarice_b200: pre-filters of more than 16 taps are not supported\n"
+                            : "deltarice_b200: invalid compression_opts (RiceParameter must be 2^k <= 32768, WaveformLength >= 1 or -1, "
+                              "filter length >= 1, first tap != 0)\n");
         return 0;
     }
     std::lock_guard<std::mutex> lock(g_mu);
     drice_ctx *ctx = global_ctx();
     if (!ctx) return 0;
+    // the pre-filter of THIS call (cd_values[2..], src/deltaRice.c:277-290); the handle is shared by
+    // every dataset of the process and calls are serialised by g_mu
+    if (drice_set_filter(ctx, prm.filter, prm.filter_len) != DRICE_OK) {
+        fprintf(stderr, "deltarice_b200: %s\n", drice_last_error(ctx));
+        return 0;
+    }
 
     if (flags & H5Z_FLAG_REVERSE) {
         if (nbytes < 4 || (nbytes & 3)) {

@@ -12,6 +12,8 @@
  *   drice_decode_batch_*   <- readWholeCompressedByteString   src/deltaRice.c:301-358
  *                             (+ perWaveDecompression :293-297, decompressWithRiceCoding
  *                              :138-189, decodeWaveform :78-90)
+ *   drice_set_filter       <- the `filter` argument of encodeWaveform / decodeWaveform
+ *                             src/deltaRice.c:49-104 (generic branches :64-74, :91-102)
  *   drice_parse_cd_values  <- parseCD_VALUES                  src/deltaRice.c:248-291
  *   drice_log2_param       <- determinePowerOf2               src/deltaRice.c:114-136
  * The reference handles ONE chunk per call (libhdf5 calls the filter per chunk); the batch
@@ -35,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DRICE_ABI_VERSION 1
+#define DRICE_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DRICE_API __attribute__((visibility("default")))
@@ -49,7 +51,9 @@ extern "C" {
 #define DRICE_E_CAPACITY   -3   /* output buffer too small                              */
 #define DRICE_E_STREAM     -4   /* malformed compressed stream                          */
 #define DRICE_E_NOMEM      -5
-#define DRICE_E_UNSUPPORTED -6  /* generic pre-filter (cd_nelmts >= 3, not [1,-1]/[1])  */
+#define DRICE_E_UNSUPPORTED -6  /* pre-filter longer than DRICE_MAX_FILTER taps           */
+
+#define DRICE_MAX_FILTER   16   /* taps of a generic pre-filter (cd_values[3..])        */
 
 typedef struct drice_ctx drice_ctx;
 
@@ -58,7 +62,7 @@ typedef struct drice_params {
     int32_t M;          /* Rice parameter, 2^k, 1 <= M <= 32768                        */
     int32_t L;          /* WaveformLength in samples; -1 = whole chunk is one wave      */
     int32_t filter_len; /* 2 for the default delta filter [1,-1]                        */
-    int32_t filter[8];
+    int32_t filter[DRICE_MAX_FILTER];
 } drice_params;
 
 DRICE_API int drice_abi_version(void);
@@ -68,7 +72,7 @@ DRICE_API int drice_log2_param(int M);
 
 /* cd_values -> params.  n = 0: M=8, L=-1;  n = 1: (M);  n = 2: (M, L);  n >= 3: (M, L,
  * filter_len, f0, f1, ...).  Returns DRICE_OK, DRICE_E_PARAM (bad M, L == 0, L < -1,
- * filter_len <= 0) or DRICE_E_UNSUPPORTED (a filter other than the delta filter [1,-1]). */
+ * filter_len <= 0, f0 == 0) or DRICE_E_UNSUPPORTED (more than DRICE_MAX_FILTER taps). */
 DRICE_API int drice_parse_cd_values(size_t cd_nelmts, const unsigned int *cd_values, drice_params *out);
 
 /* Worst-case compressed size in BYTES of one chunk of `nsamples` int16 cut into waves of L
@@ -83,6 +87,14 @@ DRICE_API int  drice_create(drice_ctx **ctx, int device);
 DRICE_API void drice_destroy(drice_ctx *ctx);
 DRICE_API const char *drice_last_error(const drice_ctx *ctx);   /* ctx may be NULL: creation errors */
 DRICE_API int  drice_device(const drice_ctx *ctx);
+
+/* Pre-filter of the following encode / decode calls on this context (reference cd_values[2..],
+ * encodeWaveform / decodeWaveform src/deltaRice.c:49-104): `filter_len` taps.  The default
+ * (and filter == NULL) is the delta filter [1,-1], fused into the codec kernels; [1] codes the
+ * samples as they are; any other filter adds one FIR pass before encode and one recursive
+ * pass after decode, with the reference's arithmetic (sums modulo 2^16, C division by f[0]).
+ * DRICE_E_PARAM: filter_len < 1 or f[0] == 0; DRICE_E_UNSUPPORTED: > DRICE_MAX_FILTER taps. */
+DRICE_API int drice_set_filter(drice_ctx *ctx, const int32_t *filter, int filter_len);
 
 /* Pinned host memory helpers for the host-pointer entry points (optional). */
 DRICE_API void *drice_host_alloc(size_t bytes);

@@ -68,19 +68,33 @@ static inline int16_t unzigzag16(uint32_t u)
     return (u & 1u) ? (int16_t)(-(int32_t)((u + 1) >> 1)) : (int16_t)(u >> 1);
 }
 
-/* One wave: delta (reference src/deltaRice.c:53-62) + Rice pack (:205-241).
+/* Pre-filter value of sample i of a wave (reference src/deltaRice.c:49-75, encodeWaveform):
+ * the delta filter [1,-1] (f == NULL here) is d[0] = x[0], d[i] = x[i] - x[i-1] (:53-62); any
+ * other filter is the FIR sum over the taps that stay inside the wave, accumulated in a
+ * `short` (:64-74), i.e. modulo 2^16. */
+static inline int16_t prefilter_at(const int16_t *x, size_t i, const int *f, int flen)
+{
+    if (!f) return (i == 0) ? x[0] : (int16_t)(uint16_t)((uint16_t)x[i] - (uint16_t)x[i - 1]);
+    uint32_t acc = (uint32_t)((int32_t)x[i] * f[0]);
+    for (int j = 1; j < flen && (size_t)j <= i; ++j) acc += (uint32_t)((int32_t)x[i - (size_t)j] * f[j]);
+    return (int16_t)(uint16_t)acc;
+}
+
+/* is (f, flen) the delta filter?  reference src/deltaRice.c:38-46 (checkIfDeltaFilter) */
+static inline int is_delta_filter(const int *f, int flen) { return !f || (flen == 2 && f[0] == 1 && f[1] == -1); }
+
+/* One wave: pre-filter + Rice pack (:205-241).
  * Writes the code words to out[0..], returns the word count.  MSB-first packing:
  * a 64-bit shift register is drained one 32-bit word at a time (:229-235); the last
  * partial word is left-aligned with zero fill (:237-241). */
-size_t drice_oracle_encode_wave(const int16_t *x, size_t n, int k, uint32_t *out)
+static size_t encode_wave_f(const int16_t *x, size_t n, int k, const int *f, int flen, uint32_t *out)
 {
     uint64_t acc = 0;  /* low `fill` bits are pending output */
     unsigned fill = 0;
     size_t nw = 0;
-    int16_t prev = 0;
+    if (is_delta_filter(f, flen)) f = NULL;
     for (size_t i = 0; i < n; ++i) {
-        int16_t d = (i == 0) ? x[0] : (int16_t)(uint16_t)((uint16_t)x[i] - (uint16_t)prev);
-        prev = x[i];
+        int16_t d = prefilter_at(x, i, f, flen);
         uint32_t u = zigzag16(d);
         uint32_t q = u >> k;
         if (q < DRICE_ESC_Q) {                     /* q zeros, a one, k remainder bits */
@@ -100,36 +114,49 @@ size_t drice_oracle_encode_wave(const int16_t *x, size_t n, int k, uint32_t *out
     return nw;
 }
 
+size_t drice_oracle_encode_wave(const int16_t *x, size_t n, int k, uint32_t *out)
+{
+    return encode_wave_f(x, n, k, NULL, 0, out);
+}
+
 /* Chunk framing, reference src/deltaRice.c:383-436 (OpenMP branch semantics):
  *   out[0] = total samples; then per wave [nwords][words...] (:379,:415,:427-432).
  * L == 0 means "whole chunk is one wave" (WaveformLength -1, :391-393).
  * Returns words written, or 0 on error (bad M, capacity). */
-size_t drice_oracle_encode_chunk(const int16_t *x, size_t total, int M, size_t L,
-                                 uint32_t *out, size_t cap_words)
+size_t drice_oracle_encode_chunk_f(const int16_t *x, size_t total, int M, size_t L, const int *f, int flen,
+                                   uint32_t *out, size_t cap_words)
 {
     int k = drice_oracle_log2_param(M);
     if (k < 0 || total > 0x7fffffffu) return 0;
+    if (f && (flen < 1 || f[0] == 0)) return 0;      /* empty filter / division by f[0] (:100), Appendix B9 */
     if (L == 0) L = total;
     if (cap_words < drice_oracle_chunk_bound_words(total, L)) return 0;
     out[0] = (uint32_t)total;
     size_t pos = 1;
     for (size_t s = 0; s < total; s += L) {
         size_t n = total - s < L ? total - s : L;     /* short last wave, :420-422 */
-        size_t nw = drice_oracle_encode_wave(x + s, n, k, out + pos + 1);
+        size_t nw = encode_wave_f(x + s, n, k, f, flen, out + pos + 1);
         out[pos] = (uint32_t)nw;
         pos += nw + 1;
     }
     return pos;
 }
 
+size_t drice_oracle_encode_chunk(const int16_t *x, size_t total, int M, size_t L,
+                                 uint32_t *out, size_t cap_words)
+{
+    return drice_oracle_encode_chunk_f(x, total, M, L, NULL, 0, out, cap_words);
+}
+
 /* One wave: Rice parse (reference src/deltaRice.c:154-187) + inverse delta (:80-89).
  * `avail` = words available from `in` (bounds guard, reference has none: Appendix B8).
  * Returns the number of words consumed by the codes, or (size_t)-1 on a malformed
  * stream (unary run longer than 8 or reading past `avail`). */
-size_t drice_oracle_decode_wave(const uint32_t *in, size_t avail, size_t n, int k, int16_t *y)
+static size_t decode_wave_f(const uint32_t *in, size_t avail, size_t n, int k, const int *f, int flen, int16_t *y)
 {
     uint64_t pos = 0; /* bit position */
     int16_t acc = 0;
+    if (is_delta_filter(f, flen)) f = NULL;
     for (size_t i = 0; i < n; ++i) {
         unsigned q = 0;
         for (;;) {                                /* unary run, :156-159 */
@@ -148,20 +175,34 @@ size_t drice_oracle_decode_wave(const uint32_t *in, size_t avail, size_t n, int 
         }
         uint32_t u = (q == DRICE_ESC_Q) ? v : ((q << k) + v);
         int16_t d = unzigzag16(u);
-        acc = (i == 0) ? d : (int16_t)(uint16_t)((uint16_t)acc + (uint16_t)d);
+        if (!f) {
+            acc = (i == 0) ? d : (int16_t)(uint16_t)((uint16_t)acc + (uint16_t)d);
+        } else {
+            /* inverse of a generic filter, reference src/deltaRice.c:91-102 (decodeWaveform): the
+             * recursion runs in a `short` (modulo 2^16), then a C division by f[0] */
+            uint32_t t = (uint16_t)d;
+            for (int j = 1; j < flen && (size_t)j <= i; ++j) t -= (uint32_t)((int32_t)y[i - (size_t)j] * f[j]);
+            acc = (int16_t)((int32_t)(int16_t)(uint16_t)t / f[0]);
+        }
         y[i] = acc;
     }
     return (size_t)((pos + 31) >> 5);
 }
 
+size_t drice_oracle_decode_wave(const uint32_t *in, size_t avail, size_t n, int k, int16_t *y)
+{
+    return decode_wave_f(in, avail, n, k, NULL, 0, y);
+}
+
 /* Chunk decode, reference src/deltaRice.c:301-341 (OpenMP branch): total = in[0] (:306),
  * header walk cur += in[cur]+1 (:319-325), waves of L samples, last one short (:329-331).
  * Returns samples written, or (size_t)-1 on error. */
-size_t drice_oracle_decode_chunk(const uint32_t *in, size_t nwords, int M, size_t L,
-                                 int16_t *y, size_t cap_samples)
+size_t drice_oracle_decode_chunk_f(const uint32_t *in, size_t nwords, int M, size_t L, const int *f, int flen,
+                                   int16_t *y, size_t cap_samples)
 {
     int k = drice_oracle_log2_param(M);
     if (k < 0 || nwords < 1) return (size_t)-1;
+    if (f && (flen < 1 || f[0] == 0)) return (size_t)-1;
     size_t total = in[0];
     if (total > cap_samples) return (size_t)-1;
     if (L == 0) L = total;
@@ -171,11 +212,17 @@ size_t drice_oracle_decode_chunk(const uint32_t *in, size_t nwords, int M, size_
         if (cur >= nwords) return (size_t)-1;
         size_t nw = in[cur];
         if (cur + 1 + nw > nwords) return (size_t)-1;
-        size_t used = drice_oracle_decode_wave(in + cur + 1, nw, n, k, y + s);
+        size_t used = decode_wave_f(in + cur + 1, nw, n, k, f, flen, y + s);
         if (used == (size_t)-1 || used != nw) return (size_t)-1;
         cur += nw + 1;
     }
     return total;
+}
+
+size_t drice_oracle_decode_chunk(const uint32_t *in, size_t nwords, int M, size_t L,
+                                 int16_t *y, size_t cap_samples)
+{
+    return drice_oracle_decode_chunk_f(in, nwords, M, L, NULL, 0, y, cap_samples);
 }
 
 /* ---- multi-chunk helpers for the timed CPU baseline ("port" kind) ----------------

@@ -52,6 +52,10 @@ def lib() -> C.CDLL:
             f = getattr(L, name)
             f.restype = sz
             f.argtypes = [vp, sz, i, sz, vp, sz]
+        for name in ("drice_oracle_encode_chunk_f", "drice_oracle_decode_chunk_f"):
+            f = getattr(L, name)
+            f.restype = sz
+            f.argtypes = [vp, sz, i, sz, vp, i, vp, sz]
         _lib = L
     return _lib
 
@@ -64,11 +68,32 @@ def bound_words(total: int, L: int | None) -> int:
     return int(lib().drice_oracle_chunk_bound_words(total, _L(L)))
 
 
-def encode_chunk(x: np.ndarray, M: int = 8, L: int | None = None, mt: bool = False) -> np.ndarray:
-    """int16[total] -> uint32 stream words of one chunk (reference src/deltaRice.c:383-436)."""
+def _filt(filt):
+    f = np.ascontiguousarray(np.asarray(filt, dtype=np.int64).astype(np.int32))
+    return f, f.ctypes.data, int(f.size)
+
+
+def cd_values(M: int, L: int | None, filt=None) -> tuple:
+    """compression_opts tuple as h5py would pass it (ints as two's-complement unsigned;
+    reference parseCD_VALUES src/deltaRice.c:248-291): (M, L[, filter_len, f0, f1, ...])."""
+    if filt is None:
+        return (M,) if _L(L) == 0 else (M, _L(L))
+    Lv = 0xFFFFFFFF if _L(L) == 0 else _L(L)
+    return (M, Lv, len(filt)) + tuple(int(v) & 0xFFFFFFFF for v in filt)
+
+
+def encode_chunk(x: np.ndarray, M: int = 8, L: int | None = None, mt: bool = False, filt=None) -> np.ndarray:
+    """int16[total] -> uint32 stream words of one chunk (reference src/deltaRice.c:383-436).
+    `filt`: pre-filter taps (cd_values[3:], reference :64-74); None = the delta filter [1,-1]."""
     x = np.ascontiguousarray(x).view(np.int16).ravel()
     cap = bound_words(x.size, L)
     out = np.empty(cap, dtype=np.uint32)
+    if filt is not None:
+        f, fp, fl = _filt(filt)
+        n = lib().drice_oracle_encode_chunk_f(x.ctypes.data, x.size, int(M), _L(L), fp, fl, out.ctypes.data, cap)
+        if n == 0:
+            raise ValueError(f"oracle encode rejected M={M} L={L} total={x.size} filt={filt}")
+        return out[:n].copy()
     fn = lib().drice_oracle_encode_chunk_mt if mt else lib().drice_oracle_encode_chunk
     n = fn(x.ctypes.data, x.size, int(M), _L(L), out.ctypes.data, cap)
     if n == 0:
@@ -76,15 +101,20 @@ def encode_chunk(x: np.ndarray, M: int = 8, L: int | None = None, mt: bool = Fal
     return out[:n].copy()
 
 
-def decode_chunk(words: np.ndarray, M: int = 8, L: int | None = None, mt: bool = False) -> np.ndarray:
-    """uint32 stream words of one chunk -> int16[total] (reference src/deltaRice.c:301-341)."""
+def decode_chunk(words: np.ndarray, M: int = 8, L: int | None = None, mt: bool = False, filt=None) -> np.ndarray:
+    """uint32 stream words of one chunk -> int16[total] (reference src/deltaRice.c:301-341).
+    `filt`: pre-filter taps to invert (reference :91-102); None = the delta filter."""
     w = np.ascontiguousarray(words).view(np.uint32).ravel()
     if w.size < 1:
         raise ValueError("empty stream")
     total = int(w[0])
     y = np.empty(total, dtype=np.int16)
-    fn = lib().drice_oracle_decode_chunk_mt if mt else lib().drice_oracle_decode_chunk
-    n = fn(w.ctypes.data, w.size, int(M), _L(L), y.ctypes.data, total)
+    if filt is not None:
+        f, fp, fl = _filt(filt)
+        n = lib().drice_oracle_decode_chunk_f(w.ctypes.data, w.size, int(M), _L(L), fp, fl, y.ctypes.data, total)
+    else:
+        fn = lib().drice_oracle_decode_chunk_mt if mt else lib().drice_oracle_decode_chunk
+        n = fn(w.ctypes.data, w.size, int(M), _L(L), y.ctypes.data, total)
     if n == C.c_size_t(-1).value:
         raise ValueError("oracle decode: malformed stream")
     return y
@@ -240,13 +270,13 @@ def ref_filter(data: bytes | np.ndarray, cd_values=(), reverse: bool = False, ki
     return out
 
 
-def ref_encode_chunk(x: np.ndarray, M: int = 8, L: int | None = None, kind: str = "omp") -> np.ndarray:
+def ref_encode_chunk(x: np.ndarray, M: int = 8, L: int | None = None, kind: str = "omp", filt=None) -> np.ndarray:
     x = np.ascontiguousarray(x).view(np.int16).ravel()
-    cd = (M,) if _L(L) == 0 else (M, _L(L))
+    cd = cd_values(M, L, filt)
     return np.frombuffer(ref_filter(x, cd, False, kind), dtype=np.uint32).copy()
 
 
-def ref_decode_chunk(words: np.ndarray, M: int = 8, L: int | None = None, kind: str = "omp") -> np.ndarray:
+def ref_decode_chunk(words: np.ndarray, M: int = 8, L: int | None = None, kind: str = "omp", filt=None) -> np.ndarray:
     w = np.ascontiguousarray(words).view(np.uint32).ravel()
-    cd = (M,) if _L(L) == 0 else (M, _L(L))
+    cd = cd_values(M, L, filt)
     return np.frombuffer(ref_filter(w, cd, True, kind), dtype=np.int16).copy()

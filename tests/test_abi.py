@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.C_ABI_SYMBOLS)
     for s in list(declared) + _lib.H5_SYMBOLS:
         assert hasattr(L, s), s
-    assert L.drice_abi_version() == 1
+    assert L.drice_abi_version() == 2
 
 
 def test_h5_class_struct_matches_reference():
@@ -50,15 +50,20 @@ def test_parse_cd_values_defaults_and_forms():
     assert d.parse_cd_values((8, 1024, 2, 1, 0xFFFFFFFF)) == (8, 1024)   # explicit delta filter
 
 
-@pytest.mark.parametrize("cd", [(0,), (3,), (65536,), (8, 0), (8, 1024, 0), (8, 1024, 2, 1)])
+@pytest.mark.parametrize("cd", [(0,), (3,), (65536,), (8, 0), (8, 1024, 0), (8, 1024, 2, 1), (8, 1024, 2, 0, 1)])
 def test_parse_cd_values_rejects(cd):
     with pytest.raises(d.DeltaRiceError):
         d.parse_cd_values(cd)
 
 
-def test_generic_filter_is_refused_not_misencoded():
-    with pytest.raises(d.DeltaRiceError) as e:
-        d.parse_cd_values((8, 1024, 1, 1))
+def test_parse_cd_values_generic_filter():
+    """cd_nelmts >= 3 (reference src/deltaRice.c:277-290): ints arrive as two's-complement unsigned."""
+    from deltarice_b200.codec import parse_cd_values_full
+    assert parse_cd_values_full((8, 1024, 1, 1)) == (8, 1024, (1,))            # reference tests/test.py:48
+    assert parse_cd_values_full((4, 0xFFFFFFFF, 3, 1, 0xFFFFFFFE, 1)) == (4, -1, (1, -2, 1))
+    assert parse_cd_values_full((8,)) == (8, -1, (1, -1))
+    with pytest.raises(d.DeltaRiceError) as e:                                 # more taps than the kernels take
+        d.parse_cd_values((8, 1024, 17) + (1,) * 17)
     assert e.value.code == _lib.E_UNSUPPORTED
 
 

@@ -60,6 +60,75 @@ def test_golden_vectors_through_filter():
         assert np.array_equal(np.frombuffer(back, np.int16), x), name
 
 
+def _cd_split(cd):
+    cd = [int(v) for v in cd]
+    M = cd[0] if len(cd) >= 1 else 8
+    L = cd[1] if len(cd) >= 2 else None
+    if L is not None and L >= 0x80000000:
+        L = None
+    taps = None
+    if len(cd) >= 3:
+        taps = [v - (1 << 32) if v >= 0x80000000 else v for v in cd[3:3 + cd[2]]]
+    return M, L, taps
+
+
+def test_golden_filter_vectors_through_filter():
+    """compression_opts with a pre-filter (cd_nelmts >= 3, incl. the reference's own
+    tests/test.py:46-83 option tuple (8, 1024, 1, 1)): streams and decoded outputs of the
+    UNMODIFIED reference (tests/golden/make_golden_filters.py), through H5Z_filter_deltarice."""
+    from deltarice_b200 import h5
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "golden_filters_v1.npz"))
+    for name in g["names"]:
+        x, cd = g[f"{name}__x"], tuple(int(v) for v in g[f"{name}__cd"])
+        stream, back = g[f"{name}__stream"], g[f"{name}__back"]
+        got = h5.apply_filter(x.tobytes(), cd, reverse=False)
+        assert np.array_equal(np.frombuffer(got, np.uint32), stream), name
+        dec = h5.apply_filter(stream.tobytes(), cd, reverse=True)
+        assert np.array_equal(np.frombuffer(dec, np.int16), back), name
+    # and the default filter still works on the shared handle afterwards
+    x = g["second_difference__x"]
+    s = h5.apply_filter(x.tobytes(), (4, 7000), reverse=False)
+    assert h5.apply_filter(s, (4, 7000), reverse=True) == x.tobytes()
+
+
+@pytest.mark.parametrize("taps", [[1], [1, -2, 1], [-1, 1], [2, -1], [3, 1, -2, 5], [1, 0, 0, 0, 0, 0, 0, -1]],
+                         ids=lambda t: "f" + "_".join(str(v) for v in t))
+@pytest.mark.parametrize("M,L", [(8, 7000), (4, 3500), (2, 33), (16, None), (64, 8178)])
+def test_generic_filter_batch(codec, oracle, taps, M, L):
+    """Ragged multi-chunk batches with a pre-filter against the oracle (FIR before encode,
+    recursion + division after decode; reference src/deltaRice.c:64-74, :91-102)."""
+    rng = np.random.default_rng(len(taps) * 100 + M)
+    sizes = [7000 * 3, 0, 1, 3500 * 2 + 17, 8178 * 2, 64]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    x = np.cumsum(rng.normal(0, 9, int(off[-1]))).astype(np.int16)
+    x[:5000] = rng.integers(-32768, 32768, 5000)                  # escapes and wrap-around
+    codec.set_filter(taps)
+    try:
+        got, boff = codec.encode_host(x, off, M, L)
+        parts = [oracle.encode_chunk(x[int(off[c]):int(off[c + 1])], M, L, filt=taps) for c in range(len(sizes))]
+        want = np.concatenate(parts)
+        assert int(boff[-1]) == 4 * want.size
+        assert np.array_equal(got.view(np.uint32), want)
+        back = codec.decode_host(got, boff, off, M, L)
+        want_back = np.concatenate([oracle.decode_chunk(p, M, L, filt=taps) for p in parts])
+        assert np.array_equal(back, want_back)
+        if abs(taps[0]) == 1:
+            assert np.array_equal(back, x)
+    finally:
+        codec.set_filter(None)
+    # the default delta filter is back
+    got, boff = codec.encode_host(x[:7000], None, M, L)
+    assert np.array_equal(got.view(np.uint32), oracle.encode_chunk(x[:7000], M, L))
+
+
+def test_set_filter_rejects(codec):
+    import deltarice_b200 as d
+    for bad in ([], [0, 1], [1] * 17):
+        with pytest.raises(d.DeltaRiceError):
+            codec.set_filter(bad)
+    codec.set_filter(None)
+
+
 def test_readme_config_c1_batch(codec, oracle):
     """C1: (100,7000) N(0,10), M=8, chunks (20,7000): 5 chunks in ONE launch."""
     x = np.random.default_rng(0).normal(0, 10, (100, 7000)).astype(np.int16).ravel()
