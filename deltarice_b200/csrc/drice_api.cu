@@ -63,6 +63,7 @@ struct drice_ctx {
     int filter_len = 2;
     int filter[drice::kMaxFilter] = {1, -1};
     DevBuf d_filt;                       // generic filter: pre-filtered samples of the batch
+    DevBuf d_lane;                       // lane-per-wave encoder: one worst-case slot per wave
 
     // optional per-kernel timing (drice_timing_*): event pairs recorded around launches
     bool timing = false;
@@ -380,7 +381,7 @@ extern "C" void drice_destroy(drice_ctx *ctx)
     }
     for (auto &t : ctx->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
-    ctx->d_tab.release(); ctx->d_scratch.release(); ctx->d_offs.release(); ctx->d_filt.release();
+    ctx->d_tab.release(); ctx->d_scratch.release(); ctx->d_offs.release(); ctx->d_filt.release(); ctx->d_lane.release();
     if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
     if (ctx->h_sync) cudaFreeHost(ctx->h_sync);
     if (ctx->ev_tab) cudaEventDestroy(ctx->ev_tab);
@@ -443,7 +444,9 @@ extern "C" int drice_timing_read(drice_ctx *ctx, double *ms, uint64_t *launches,
 
 extern "C" const char *drice_kernel_name(int kind)
 {
-    static const char *names[DRICE_NUM_KERNELS] = {"encode_tile_kernel", "locate_kernel", "parse_kernel"};
+    // kind 0 = the encode kernel of the batch: encode_lane_kernel (>= DRICE_ENC_LANE_MIN waves), else
+    // encode_tile_kernel / encode_multi_kernel
+    static const char *names[DRICE_NUM_KERNELS] = {"encode_kernel", "locate_kernel", "parse_kernel"};
     return (kind >= 0 && kind < DRICE_NUM_KERNELS) ? names[kind] : nullptr;
 }
 
@@ -484,9 +487,12 @@ extern "C" int drice_encode_batch_dev_async(drice_ctx *ctx, const int16_t *d_raw
     uint32_t *d_woff;
     rc = upload_tables(ctx, off, nullptr, g.wave_off.data(), nchunks, st, &d_soff, &d_unused, &d_woff);
     if (rc) return rc;
-    // scratch: [ticket u32][pad] | look-back status u64 per tile (at most one per wave), zeroed
-    const size_t zeroed = (size_t)g.nwaves * 8 + 16;
-    const size_t scratch = zeroed;
+    // scratch: [ticket u32][pad] | look-back status u64 per tile (at most one per wave) | slices done
+    // u32 per lane-kernel task: all zeroed; then the parked lane states (not zeroed)
+    const size_t ntasks = ((size_t)g.nwaves + 31) / 32;
+    const size_t zeroed = (size_t)g.nwaves * 8 + 16 + ntasks * 4 + 16;
+    const size_t state_off = (zeroed + 255) & ~(size_t)255;
+    const size_t scratch = state_off + ntasks * 6 * 32 * 4;
     if (scratch > ctx->d_scratch.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
     DR_CUDA(ctx, ctx->d_scratch.reserve(scratch));
     DR_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch.p, 0, zeroed, st));
@@ -526,6 +532,25 @@ extern "C" int drice_encode_batch_dev_async(drice_ctx *ctx, const int16_t *d_raw
     p.uniform_wpc = g.uniform_wpc;
     p.L = g.Lk;
     p.k = k;
+    // enough waves to fill the machine with one LANE per wave (and a scratch that stays reasonable):
+    // the lane kernel; otherwise one warp per wave
+    {
+        static long lane_min = -1;
+        if (lane_min < 0) {
+            const char *e = getenv("DRICE_ENC_LANE_MIN");
+            lane_min = e ? atol(e) : 100000;
+        }
+        const uint64_t slot = ((25ull * g.max_wave + 31ull) / 32ull + 7ull) & ~7ull;
+        const uint64_t bytes = slot * 4ull * g.nwaves;
+        if ((long)g.nwaves >= lane_min && g.max_wave > 0 && slot < (1ull << 31) && bytes <= (24ull << 30)) {
+            if (bytes > ctx->d_lane.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
+            DR_CUDA(ctx, ctx->d_lane.reserve((size_t)bytes));
+            p.lane_scratch = (uint32_t *)ctx->d_lane.p;
+            p.lane_slot_words = (uint32_t)slot;
+            p.lane_slice_done = (uint32_t *)((char *)ctx->d_scratch.p + 16 + (size_t)g.nwaves * 8);
+            p.lane_state = (uint32_t *)((char *)ctx->d_scratch.p + state_off);
+        }
+    }
     int nl;
     {
         TimedScope ts(ctx, DRICE_KERNEL_ENCODE, st);

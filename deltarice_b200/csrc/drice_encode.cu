@@ -232,6 +232,7 @@ __device__ __forceinline__ void load_slot_tail(RawWords &r, const int16_t *q, ui
 
 // exclusive word offset of tile g among all tiles: decoupled look-back by one warp, four rows of
 // 32 status words in flight per round trip.  The tile's own aggregate is already published.
+template <int kSleepNs = 200>
 __device__ __forceinline__ uint64_t lookback_excl(uint64_t *lookback, uint32_t g, uint64_t mine, int lane)
 {
     uint64_t excl = 0;
@@ -263,7 +264,7 @@ __device__ __forceinline__ uint64_t lookback_excl(uint64_t *lookback, uint32_t g
                         done = pm != 0;
                         break;
                     }
-                    __nanosleep(200);
+                    __nanosleep(kSleepNs);
                     if ((v >> 62) == 0) v = ld_relaxed_u64(lookback + my);
                 }
             }
@@ -636,6 +637,350 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
     }
 }
 
+// zig-zag of the 16-bit wrapped difference cur-prev (src/deltaRice.c:57-62, :207-211)
+__device__ __forceinline__ uint32_t zigzag_delta(int cur, int prev)
+{
+    const int t = cur - prev;
+    const uint32_t s = (uint32_t)((int)((uint32_t)t << 16) >> 31);
+    return (((uint32_t)t << 1) ^ s) & 0xFFFFu;
+}
+
+// ======================================================================================
+// lane kernel: one LANE per wave (large batches)
+// ======================================================================================
+// With hundreds of thousands of waves in a batch the parallelism is across waves, as in the
+// decoder: every lane encodes its OWN wave sequentially, so nothing is shared inside a wave -
+// no per-round warp scan, no stitching of neighbouring lanes' bits, no warp-uniform escape
+// handling: delta / zig-zag on packed halves, pair codes, and the multiply-append packer are the
+// whole loop (17 instead of 31 instructions per sample).  The price is that a wave's size is only
+// known when it is done, so the lane first packs into a worst-case sized SLOT of an HBM scratch
+// (32-byte sectors, through a 32-word ring in shared memory), and when the 32 waves of the warp
+// task are finished the warp resolves the task's offset by decoupled look-back over TASKS and
+// copies the records to their final place, coalesced (the slots are still in L2 for the most part).
+//   input:  one 32-byte sector per lane and 16 samples, requested a block ahead;
+//   output: ring[word][lane] (bank = lane), flushed as full sectors.
+constexpr int kLaneWarps = 17;               // per CTA; two CTAs per SM
+constexpr int kLaneRingWords = 32;           // per lane
+
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+struct Sector { uint32_t w[8]; };
+__device__ __forceinline__ Sector ldg_sector(const void *p)
+{
+    Sector r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_sector(void *p, const uint32_t (&v)[8])
+{
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ uint32_t ldg_cg_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ldg_cg_v4(const uint32_t *p)
+{
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+// bit packer of one lane over its whole wave (same multiply-append as Packer); finished words go
+// to the lane's ring, full sectors of the ring to the wave's scratch slot
+struct LanePacker {
+    uint32_t lo, n;             // pending bits in the low n (< 32) bits of lo
+    uint32_t wcount;            // words produced so far
+    uint32_t flushed;           // words already in the slot (multiple of 8)
+    uint32_t ring_b;            // shared address of the lane's ring row 0
+    uint32_t *slot;
+
+    __device__ __forceinline__ void put(uint32_t v, uint32_t len)
+    {
+        const uint64_t a = mul_wide(lo, pow2(len));
+        const uint32_t alo = (uint32_t)a | v;
+        n += len;
+        if (n >= 32u) {
+            n -= 32u;
+            sts32(ring_b + ((wcount & (kLaneRingWords - 1u)) << 7), __funnelshift_r(alo, (uint32_t)(a >> 32), n));
+            ++wcount;
+        }
+        lo = alo;
+    }
+    __device__ __forceinline__ void flush_sectors()
+    {
+        while (wcount - flushed >= 8u) {
+            const uint32_t ad = ring_b + ((flushed & (kLaneRingWords - 1u)) << 7);
+            uint32_t v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = lds32(ad + 128u * i);
+            stg_sector(slot + flushed, v);
+            flushed += 8u;
+        }
+    }
+    // closes the wave: the last partial word is left aligned, zero padded (:237-241)
+    __device__ __forceinline__ uint32_t finish()
+    {
+        if (n) {
+            uint32_t last;
+            asm("shl.b32 %0, %1, %2;" : "=r"(last) : "r"(lo), "r"(32u - n));
+            sts32(ring_b + ((wcount & (kLaneRingWords - 1u)) << 7), last);
+            ++wcount;
+        }
+        flush_sectors();
+        for (uint32_t i = flushed; i < wcount; ++i) slot[i] = lds32(ring_b + ((i & (kLaneRingWords - 1u)) << 7));
+        return wcount;
+    }
+};
+
+// one sample through the generic code (prologue / epilogue of a wave, escapes)
+template <int K>
+__device__ __forceinline__ void lane_put_sample(LanePacker &pk, uint32_t u)
+{
+    uint32_t v, l;
+    rice_code<K>(u, v, l);
+    pk.put(v, l);
+}
+
+// Work is handed out in SLICES: an item = (task of 32 waves, slice of kLaneSliceBlocks * 16 samples),
+// tickets run slice-major (every task's slice 0, then every task's slice 1, ...), and a lane's state
+// (packer, previous sample, position; the < 8 words still in its ring go to the slot) is parked in
+// global memory between slices.  With one long task per warp the SM's warp scheduler favours its
+// older CTA: that CTA's tasks finished ~170 us before the other's and half of the machine then ran at
+// half its warps and half its IPC (measured with per-task timestamps).  Slices keep all tasks in lock
+// step, so every warp has work until the end, whatever the number of tasks per warp.
+constexpr uint32_t kLaneSliceBlocks = 32;     // 512 samples per slice
+constexpr int      kLaneStateWords  = 6;      // per lane: lo, n, wcount, flushed, previous sample, samples done
+
+template <int K>
+__global__ void __launch_bounds__(kLaneWarps * 32, 2)
+encode_lane_kernel(const EncodeParams p, uint32_t *const scratch, const uint32_t slot_words, const uint32_t ngroups,
+                   const uint32_t nslices, uint32_t *const state, uint32_t *const slice_done)
+{
+    using C = RiceConst<K>;
+    constexpr bool kPairs = C::kPairs;
+    constexpr uint32_t M = C::M;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t ring_b = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)warp * (kLaneRingWords * 128u) + (uint32_t)lane * 4u;
+    asm volatile("mov.u32 %0, %0;" : "+r"(ring_b));         // keep it in a register (not recomputed per word)
+    const int16_t *const raw_hi = p.raw + p.raw_samples;
+    const int dmask = (int)p.neg_prev;                      // -1: delta, 0: none
+    const uint32_t nitems = ngroups * nslices;
+
+    while (true) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(p.ticket, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nitems) break;
+        const uint32_t slice = item / ngroups;
+        const uint32_t grp = item - slice * ngroups;
+        const bool last_slice = slice == nslices - 1;
+        const uint32_t g = grp * 32u + (uint32_t)lane;
+        const bool active = g < p.nwaves;
+        WaveGeom wg;
+        wg.begin = 0; wg.n = 0; wg.chunk = 0; wg.first = 0; wg.chunk_total = 0; wg.g = g; wg.pad_ = 0;
+        if (active) wg = locate_wave(p, g);
+        const uint32_t n = wg.chunk_total ? wg.n : 0u;
+
+        LanePacker pk;
+        pk.lo = 0; pk.n = 0; pk.wcount = 0; pk.flushed = 0;
+        pk.ring_b = ring_b;
+        pk.slot = scratch + (size_t)g * slot_words;
+        int prevs = 0;                                       // previous sample of the wave
+        uint32_t done = 0;                                   // samples of the wave already coded
+        uint32_t *const st = state + ((size_t)grp * kLaneStateWords) * 32u + (uint32_t)lane;
+        __syncwarp();
+        if (slice) {
+            // the task's previous slice (handed out ngroups tickets ago) must have parked its state
+            if (lane == 0) {
+                while (ld_acquire_u32(slice_done + grp) < slice) __nanosleep(100);
+            }
+            __syncwarp();
+            pk.lo = ldg_cg_u32(st);
+            pk.n = ldg_cg_u32(st + 32);
+            pk.wcount = ldg_cg_u32(st + 64);
+            pk.flushed = ldg_cg_u32(st + 96);
+            prevs = (int)ldg_cg_u32(st + 128);
+            done = ldg_cg_u32(st + 160);
+            if (n) for (uint32_t i = pk.flushed; i < pk.wcount; ++i) sts32(ring_b + ((i & (kLaneRingWords - 1u)) << 7), ldg_cg_u32(pk.slot + i));
+        }
+        const int16_t *q = p.raw + wg.begin + done;
+        uint32_t left = n - done;
+
+        // ---- prologue (slice 0): single samples up to the first 32-byte boundary of the input -----
+        if (slice == 0) {
+            uint32_t pro = (uint32_t)((32u - (uint32_t)(reinterpret_cast<uintptr_t>(q) & 31u)) & 31u) >> 1;
+            if (pro > left) pro = left;
+            left -= pro;
+            done += pro;
+            for (; pro; --pro) {
+                const int x = *q++;
+                lane_put_sample<K>(pk, zigzag_delta(x, prevs & dmask));
+                prevs = x;
+            }
+        }
+        // ---- blocks of 16 samples = one sector ----------------------------------------------------
+        uint32_t nblk = left >> 4;
+        if (nblk > kLaneSliceBlocks) nblk = kLaneSliceBlocks;
+        const uint32_t maxblk = __reduce_max_sync(0xffffffffu, nblk);
+        uint32_t pw = (uint32_t)prevs << 16;                 // previous sample in the HIGH half
+        Sector nxt;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) nxt.w[m] = 0;
+        if (nblk) nxt = ldg_sector(q);
+        const uint32_t MMr = opaque(C::MM), NNr = opaque(C::NN);
+        for (uint32_t b = 0; b < maxblk; ++b) {
+            if (b < nblk) {
+                const Sector cur = nxt;
+                q += 16;
+                if (b + 1 < nblk) nxt = ldg_sector(q);
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    // delta + zig-zag on packed halves (src/deltaRice.c:57-62, :207-211)
+                    const uint32_t prev = m ? cur.w[m - 1] : pw;
+                    const uint32_t X = cur.w[m] * p.mul_x;
+                    const uint32_t Y = mad_lo(prev >> 16, p.neg_prev, cur.w[m]);
+                    const uint32_t D = prmt(Y, X, 0x7610);
+                    const uint32_t Sg = prmt(D, 0, 0xbb99);
+                    const uint32_t u2 = __vadd2(D, D) ^ Sg;
+                    if (kPairs) {
+                        if ((u2 & C::HM) == 0u) {            // two samples as one code of <= 30 bits
+                            const uint32_t V2 = (u2 | MMr) & NNr;
+                            const uint32_t qhi = u2 >> (16 + K), qlo = (u2 >> K) & C::QM;
+                            pk.put(mad_lo(V2 & 0xFFFFu, (2u * M) << qhi, V2 >> 16), qlo + qhi + 2u * (K + 1));
+                        } else {                             // a quotient >= 8: escape code(s)
+                            lane_put_sample<K>(pk, u2 & 0xFFFFu);
+                            lane_put_sample<K>(pk, u2 >> 16);
+                        }
+                    } else {
+                        lane_put_sample<K>(pk, u2 & 0xFFFFu);
+                        lane_put_sample<K>(pk, u2 >> 16);
+                    }
+                }
+                pw = cur.w[7];
+                pk.flush_sectors();
+            }
+        }
+        if (nblk) prevs = (int)pw >> 16;
+        done += nblk * 16u;
+        left -= nblk * 16u;
+
+        if (!last_slice) {
+            // ---- park the lane: pending words to the slot, state to global memory -----------------
+            if (n) for (uint32_t i = pk.flushed; i < pk.wcount; ++i) pk.slot[i] = lds32(ring_b + ((i & (kLaneRingWords - 1u)) << 7));
+            st[0] = pk.lo;
+            st[32] = pk.n;
+            st[64] = pk.wcount;
+            st[96] = pk.flushed;
+            st[128] = (uint32_t)prevs;
+            st[160] = done;
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_release_u32(slice_done + grp, slice + 1u);
+            continue;
+        }
+        // ---- epilogue (last slice): the last < 16 samples ----------------------------------------------
+        for (; left; --left) {
+            const int x = (q < raw_hi) ? (int)*q : 0;
+            ++q;
+            lane_put_sample<K>(pk, zigzag_delta(x, prevs & dmask));
+            prevs = x;
+        }
+        const uint32_t nwords = n ? pk.finish() : 0u;
+        __syncwarp();
+
+        // ---- the task's 32 records -> their final place --------------------------------------------
+        // (the last slices are handed out in task order, so the look-back finds its prefix close by)
+        const uint32_t rec_words = (active && wg.chunk_total) ? nwords + 1u : 0u;
+        const uint32_t mine = rec_words + (active ? wg.first : 0u);     // empty chunk: header only
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) st_relaxed_u64(p.lookback + grp, kFlagAggregate | (uint64_t)total);
+        const uint64_t excl = lookback_excl<400>(p.lookback, grp, total, lane);
+        const uint64_t off = excl + incl - mine;
+        const bool fits = off + mine <= p.out_cap_words;
+        if (!fits && mine) atomicOr(p.status, kErrCapacity);
+        if (grp == ngroups - 1 && lane == 31) p.chunk_byte_off[p.nchunks] = (excl + total) * 4;
+        if (active && wg.first) p.chunk_byte_off[wg.chunk] = off * 4;
+        if (active && fits) {
+            if (wg.first) p.out[off] = wg.chunk_total;
+            if (rec_words) p.out[off + wg.first] = nwords;
+        }
+        const uint64_t dst0 = off + wg.first + 1u;
+        const uint32_t ncopy = (fits && rec_words) ? nwords : 0u;
+        // 16 bytes per lane and load, 512 words of a record per step; the loads of the next record
+        // are in flight while the current one is stored (the copy is latency bound otherwise)
+        auto load4 = [&](uint4 (&v)[4], int s, uint32_t ns, uint32_t i0) {
+            const uint32_t *src = scratch + (size_t)(grp * 32u + (uint32_t)s) * slot_words;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t idx = i0 + (uint32_t)u * 128u + (uint32_t)lane * 4u;
+                v[u] = idx < ns ? ldg_cg_v4(src + idx) : make_uint4(0, 0, 0, 0);   // (slots are padded to 8 words)
+            }
+        };
+        auto store4 = [&](const uint4 (&v)[4], uint64_t ds, uint32_t ns, uint32_t i0) {
+            uint32_t *dst = p.out + ds;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t idx = i0 + (uint32_t)u * 128u + (uint32_t)lane * 4u;
+                if (idx + 4u <= ns) {
+                    dst[idx] = v[u].x; dst[idx + 1] = v[u].y; dst[idx + 2] = v[u].z; dst[idx + 3] = v[u].w;
+                } else if (idx < ns) {
+                    dst[idx] = v[u].x;
+                    if (idx + 1 < ns) dst[idx + 1] = v[u].y;
+                    if (idx + 2 < ns) dst[idx + 2] = v[u].z;
+                }
+            }
+        };
+        uint4 cur4[4], nxt4[4];
+        uint32_t ns = __shfl_sync(0xffffffffu, ncopy, 0);
+        load4(cur4, 0, ns, 0);
+        for (int s2 = 0; s2 < 32; ++s2) {
+            const uint64_t ds = __shfl_sync(0xffffffffu, dst0, s2);
+            const uint32_t ns_next = s2 < 31 ? __shfl_sync(0xffffffffu, ncopy, (s2 + 1) & 31) : 0u;
+            if (s2 < 31) load4(nxt4, s2 + 1, ns_next, 0);
+            store4(cur4, ds, ns, 0);
+            for (uint32_t i0 = 512u; i0 < ns; i0 += 512u) {     // records of more than 512 words
+                load4(cur4, s2, ns, i0);
+                store4(cur4, ds, ns, i0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cur4[u] = nxt4[u];
+            ns = ns_next;
+        }
+        __syncwarp();
+    }
+}
+
 // ======================================================================================
 // multi-tile kernel (waves longer than one tile): generic per-sample code path
 // ======================================================================================
@@ -645,14 +990,6 @@ __device__ __forceinline__ int4 ld_stream_v4(const int4 *p)
     asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
-}
-
-// zig-zag of the 16-bit wrapped difference cur-prev (src/deltaRice.c:57-62, :207-211)
-__device__ __forceinline__ uint32_t zigzag_delta(int cur, int prev)
-{
-    const int t = cur - prev;
-    const uint32_t s = (uint32_t)((int)((uint32_t)t << 16) >> 31);
-    return (((uint32_t)t << 1) ^ s) & 0xFFFFu;
 }
 
 template <int K>
@@ -900,6 +1237,29 @@ int launch_k(const EncodeParams &p, uint32_t max_wave_len, cudaStream_t st)
     const size_t smem_multi = (size_t)(kEncMaxThreads * 13 + 1 + 2 * kEncMaxThreads + 33 + 3) * sizeof(uint32_t);
     if (max_wave_len > (uint32_t)kEncTileMaxL) {
         encode_multi_kernel<K><<<p.nwaves, kEncMaxThreads, smem_multi, st>>>(p);
+        return 1;
+    }
+    // large batches: one lane per wave (needs a worst-case sized scratch slot per wave)
+    if (p.lane_scratch && p.lane_slot_words) {
+        static bool attr_lane = false;
+        const size_t smem_lane = (size_t)kLaneWarps * kLaneRingWords * 128;
+        if (!attr_lane) {
+            cudaFuncSetAttribute(encode_lane_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lane);
+            cudaFuncSetAttribute(encode_lane_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            attr_lane = true;
+        }
+        const uint32_t ngroups = (p.nwaves + 31u) / 32u;
+        uint32_t nslices = (max_wave_len / 16u + kLaneSliceBlocks - 1u) / kLaneSliceBlocks;
+        if (nslices < 1u) nslices = 1u;
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encode_lane_kernel<K>, kLaneWarps * 32, smem_lane);
+        if (occ < 1) occ = 1;
+        if (occ > 2) occ = 2;
+        uint32_t grid = (uint32_t)(occ * g_num_sms);
+        const uint32_t need = (ngroups + kLaneWarps - 1) / kLaneWarps;
+        if (grid > need) grid = need;
+        encode_lane_kernel<K><<<grid, kLaneWarps * 32, smem_lane, st>>>(p, p.lane_scratch, p.lane_slot_words, ngroups, nslices,
+                                                                      p.lane_state, p.lane_slice_done);
         return 1;
     }
     // per-warp staging (two buffers per worker warp): room for ~10 bits per sample, at most the

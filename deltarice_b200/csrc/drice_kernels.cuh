@@ -45,6 +45,12 @@ struct EncodeParams {
     // pre-filter mode: delta (src/deltaRice.c:53-62) = (0xFFFF0001, 0xFFFFFFFF); none = (1, 0):
     // the samples are Rice-coded as they are (filter [1], or already filtered by prefilter_kernel)
     uint32_t        mul_x, neg_prev;
+    // lane-per-wave encoder (large batches): scratch of nwaves slots of lane_slot_words words
+    // (worst case of a wave, multiple of 8); null = warp-per-wave tile kernel
+    uint32_t       *lane_scratch;
+    uint32_t        lane_slot_words;
+    uint32_t       *lane_state;         // [ntasks][6][32]: lane state parked between time slices
+    uint32_t       *lane_slice_done;    // [ntasks], zeroed: slices a task has finished
 };
 
 // generic pre-filter (src/deltaRice.c:64-74 / :91-102), taps by value

@@ -129,6 +129,23 @@ def test_set_filter_rejects(codec):
     codec.set_filter(None)
 
 
+def test_lane_encoder_on_the_small_cases():
+    """Large batches are encoded by encode_lane_kernel (one lane per wave), small ones by
+    encode_tile_kernel (one warp per wave).  DRICE_ENC_LANE_MIN=1 (read once per process) sends
+    EVERY batch to the lane kernel: the edge-case suite must stay bit-exact there too."""
+    import subprocess
+    import sys
+    if os.environ.get("DRICE_ENC_LANE_MIN"):
+        pytest.skip("already running under the override")
+    env = dict(os.environ, DRICE_ENC_LANE_MIN="1")
+    sel = ("single_chunk_host_path or single_chunk_h5z_filter or golden or ragged_batch or generic_filter_batch "
+           "or unaligned_pointers or many_chunks or readme_config or errors")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", sel],
+                       env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout
+
+
 def test_readme_config_c1_batch(codec, oracle):
     """C1: (100,7000) N(0,10), M=8, chunks (20,7000): 5 chunks in ONE launch."""
     x = np.random.default_rng(0).normal(0, 10, (100, 7000)).astype(np.int16).ravel()
