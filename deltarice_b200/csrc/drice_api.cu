@@ -516,8 +516,8 @@ extern "C" int drice_encode_batch_dev_async(drice_ctx *ctx, const int16_t *d_raw
     }
     EncodeParams p{};
     p.raw = src;
-    p.mul_x = ctx->filter_mode == 0 ? 0xFFFF0001u : 1u;
-    p.neg_prev = ctx->filter_mode == 0 ? 0xFFFFFFFFu : 0u;
+    EncodeMode md{};
+    md.delta = ctx->filter_mode == 0;
     p.raw_samples = off[nchunks];
     p.out = d_out;
     p.out_cap_words = out_cap_bytes / 4;
@@ -547,16 +547,16 @@ extern "C" int drice_encode_batch_dev_async(drice_ctx *ctx, const int16_t *d_raw
         if ((long)g.nwaves >= lane_min && g.max_wave > 0 && slot < (1ull << 31) && bytes <= (24ull << 30)) {
             if (bytes > ctx->d_lane.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
             DR_CUDA(ctx, ctx->d_lane.reserve((size_t)bytes));
-            p.lane_scratch = (uint32_t *)ctx->d_lane.p;
-            p.lane_slot_words = (uint32_t)slot;
-            p.lane_slice_done = (uint32_t *)((char *)ctx->d_scratch.p + 16 + (size_t)g.nwaves * 8);
-            p.lane_state = (uint32_t *)((char *)ctx->d_scratch.p + state_off);
+            md.lane_scratch = (uint32_t *)ctx->d_lane.p;
+            md.lane_slot_words = (uint32_t)slot;
+            md.lane_slice_done = (uint32_t *)((char *)ctx->d_scratch.p + 16 + (size_t)g.nwaves * 8);
+            md.lane_state = (uint32_t *)((char *)ctx->d_scratch.p + state_off);
         }
     }
     int nl;
     {
         TimedScope ts(ctx, DRICE_KERNEL_ENCODE, st);
-        nl = launch_encode(p, g.max_wave, st);
+        nl = launch_encode(p, md, g.max_wave, st);
     }
     if (nl < 0) return fail(ctx, DRICE_E_PARAM, "unsupported RiceParameter");
     ctx->launches += (uint64_t)nl;

@@ -292,10 +292,10 @@ struct SweepState {
 };
 
 // One round = 512 samples = 16 per lane.  kFull: every lane holds 16 valid samples.
-template <int K, bool kDirect, bool kFull>
-__device__ __forceinline__ void encode_round(const EncodeParams &p, RawWords &cur, uint32_t nvalid, bool last_lane, int lane,
+template <int K, bool kDirect, bool kFull, bool kDelta>
+__device__ __forceinline__ void encode_round(RawWords &cur, uint32_t nvalid, bool last_lane, int lane,
                                              uint32_t *dst, uint32_t cap, SweepState &st)
-{   // p.mul_x / p.neg_prev (read straight from the parameter bank): the pre-filter mode
+{   // kDelta: the delta pre-filter (src/deltaRice.c:53-62); false: the samples are coded as they are
     using C = RiceConst<K>;
     constexpr bool kPairs = C::kPairs;
     constexpr uint32_t M = C::M;
@@ -304,7 +304,7 @@ __device__ __forceinline__ void encode_round(const EncodeParams &p, RawWords &cu
     // and are cut off below
     // (no pre-filter: the padding samples are zero instead, which codes the same K+1 bits)
     if (!kFull && nvalid > 0 && nvalid < (uint32_t)S) {
-        const uint32_t sel_hi = p.neg_prev ? 0x1010u : 0x4410u, sel_all = p.neg_prev ? 0x3232u : 0x4444u;
+        const uint32_t sel_hi = kDelta ? 0x1010u : 0x4410u, sel_all = kDelta ? 0x3232u : 0x4444u;
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
             if (2u * v + 1 == nvalid) w[v] = prmt(w[v], 0, sel_hi);
@@ -323,8 +323,8 @@ __device__ __forceinline__ void encode_round(const EncodeParams &p, RawWords &cu
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
         const uint32_t prev = m ? w[m - 1] : pw;
-        const uint32_t X = w[m] * p.mul_x;                  // high half: hi(w) - lo(w)   [no delta: hi(w)]
-        const uint32_t Y = mad_lo(prev >> 16, p.neg_prev, w[m]);   // low half: lo(w) - hi(prev)   [no delta: lo(w)]
+        const uint32_t X = kDelta ? w[m] * 0xFFFF0001u : w[m];      // high half: hi(w) - lo(w)
+        const uint32_t Y = kDelta ? w[m] - (prev >> 16) : w[m];     // low half:  lo(w) - hi(prev)
         const uint32_t D = prmt(Y, X, 0x7610);
         const uint32_t Sg = prmt(D, 0, 0xbb99);             // per-half sign mask
         U[m] = __vadd2(D, D) ^ Sg;
@@ -454,8 +454,8 @@ __device__ __forceinline__ void encode_round(const EncodeParams &p, RawWords &cu
 // when the wave outgrows it, packing stops (sizing continues) and *overflow is set.
 // kDirect = true: packs straight into the record in HBM, `cap` = the wave's word count (nothing
 // is stored past it).  Returns the wave's bit count.
-template <int K, bool kDirect>
-__device__ __forceinline__ uint32_t encode_wave(const EncodeParams &p, const int16_t *wave, uint32_t n, const int16_t *raw_hi, int lane,
+template <int K, bool kDirect, bool kDelta>
+__device__ __forceinline__ uint32_t encode_wave(const int16_t *wave, uint32_t n, const int16_t *raw_hi, int lane,
                                                 uint32_t *dst, uint32_t cap, bool *overflow)
 {
     const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(wave) & 15u) >> 1);
@@ -482,9 +482,9 @@ __device__ __forceinline__ uint32_t encode_wave(const EncodeParams &p, const int
         RawWords now = cur;
         q += kRound;
         if (r + 1 < nfull) load_slot(cur, q, mis); else load_slot_tail(cur, wave + tail_s0, mis, tail_valid, raw_hi);
-        encode_round<K, kDirect, true>(p, now, S, false, lane, dst, cap, st);
+        encode_round<K, kDirect, true, kDelta>(now, S, false, lane, dst, cap, st);
     }
-    encode_round<K, kDirect, false>(p, cur, tail_valid, tail_valid > 0 && tail_s0 + S >= n, lane, dst, cap, st);
+    encode_round<K, kDirect, false, kDelta>(cur, tail_valid, tail_valid > 0 && tail_s0 + S >= n, lane, dst, cap, st);
     __syncwarp();
     *overflow = st.ovf;
     return st.base;
@@ -504,7 +504,7 @@ __device__ __forceinline__ uint32_t encode_wave(const EncodeParams &p, const int
 // done with it.
 constexpr int kRing = 3;
 
-template <int K, int MINB>
+template <int K, int MINB, bool kDelta>
 __global__ void __launch_bounds__((kEncWarps + 1) * 32, MINB)
 encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint32_t ntiles)
 {
@@ -565,7 +565,7 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
                 have = true;
                 wg = locate_wave(p, g);
                 if (wg.chunk_total) {
-                    nwords = (encode_wave<K, false>(p, p.raw + wg.begin, wg.n, raw_hi, lane, stage0 + par * stage_words,
+                    nwords = (encode_wave<K, false, kDelta>(p.raw + wg.begin, wg.n, raw_hi, lane, stage0 + par * stage_words,
                                                     stage_words, &ovf) + 31u) >> 5;
                     mine = nwords + 1u;
                 }
@@ -620,7 +620,7 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
                         for (uint32_t i = lane; i < nwords_prev; i += 32) rec[1 + i] = src[i];
                     } else {                                 // larger than the staging: pack in place
                         bool dummy;
-                        encode_wave<K, true>(p, p.raw + wg_prev.begin, wg_prev.n, raw_hi, lane, rec + 1, nwords_prev, &dummy);
+                        encode_wave<K, true, kDelta>(p.raw + wg_prev.begin, wg_prev.n, raw_hi, lane, rec + 1, nwords_prev, &dummy);
                     }
                 }
             }
@@ -778,8 +778,9 @@ constexpr int      kLaneStateWords  = 6;      // per lane: lo, n, wcount, flushe
 template <int K>
 __global__ void __launch_bounds__(kLaneWarps * 32, 2)
 encode_lane_kernel(const EncodeParams p, uint32_t *const scratch, const uint32_t slot_words, const uint32_t ngroups,
-                   const uint32_t nslices, uint32_t *const state, uint32_t *const slice_done)
-{
+                   const uint32_t nslices, uint32_t *const state, uint32_t *const slice_done, const uint32_t mul_x,
+                   const uint32_t neg_prev)
+{   // (mul_x, neg_prev): pre-filter mode, delta = (0xFFFF0001, 0xFFFFFFFF), none = (1, 0)
     using C = RiceConst<K>;
     constexpr bool kPairs = C::kPairs;
     constexpr uint32_t M = C::M;
@@ -788,7 +789,7 @@ encode_lane_kernel(const EncodeParams p, uint32_t *const scratch, const uint32_t
     uint32_t ring_b = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)warp * (kLaneRingWords * 128u) + (uint32_t)lane * 4u;
     asm volatile("mov.u32 %0, %0;" : "+r"(ring_b));         // keep it in a register (not recomputed per word)
     const int16_t *const raw_hi = p.raw + p.raw_samples;
-    const int dmask = (int)p.neg_prev;                      // -1: delta, 0: none
+    const int dmask = (int)neg_prev;                        // -1: delta, 0: none
     const uint32_t nitems = ngroups * nslices;
 
     while (true) {
@@ -862,8 +863,8 @@ encode_lane_kernel(const EncodeParams p, uint32_t *const scratch, const uint32_t
                 for (int m = 0; m < 8; ++m) {
                     // delta + zig-zag on packed halves (src/deltaRice.c:57-62, :207-211)
                     const uint32_t prev = m ? cur.w[m - 1] : pw;
-                    const uint32_t X = cur.w[m] * p.mul_x;
-                    const uint32_t Y = mad_lo(prev >> 16, p.neg_prev, cur.w[m]);
+                    const uint32_t X = cur.w[m] * mul_x;
+                    const uint32_t Y = mad_lo(prev >> 16, neg_prev, cur.w[m]);
                     const uint32_t D = prmt(Y, X, 0x7610);
                     const uint32_t Sg = prmt(D, 0, 0xbb99);
                     const uint32_t u2 = __vadd2(D, D) ^ Sg;
@@ -1165,7 +1166,7 @@ __device__ __forceinline__ void pack_wave_streaming(const int16_t *wave, uint32_
 // waves longer than one warp-kernel wave: one CTA per wave, sizing sweep + look-back + packing sweep
 template <int K>
 __global__ void __launch_bounds__(kEncMaxThreads)
-encode_multi_kernel(const EncodeParams p)
+encode_multi_kernel(const EncodeParams p, const int dmask)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const int NT = blockDim.x;
@@ -1187,7 +1188,7 @@ encode_multi_kernel(const EncodeParams p)
     // ---- sizing sweep ----------------------------------------------------------------
     uint64_t bits = 0;
     for (uint32_t t = 0; t < ntiles; ++t)
-        bits += slot_codes<K>(wave, ((int64_t)t * NT + tid) * S - mis, wg.n, cv, (int)p.neg_prev);
+        bits += slot_codes<K>(wave, ((int64_t)t * NT + tid) * S - mis, wg.n, cv, dmask);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
     uint64_t *s64 = reinterpret_cast<uint64_t *>(smem);
@@ -1220,13 +1221,13 @@ encode_multi_kernel(const EncodeParams p)
         if (rec_words) rec[0] = nwords;
     }
     if (rec_words == 0) return;
-    pack_wave_streaming<K>(wave, wg.n, rec, smem, (int)p.neg_prev);
+    pack_wave_streaming<K>(wave, wg.n, rec, smem, dmask);
 }
 
 int g_num_sms = 0;
 
 template <int K>
-int launch_k(const EncodeParams &p, uint32_t max_wave_len, cudaStream_t st)
+int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len, cudaStream_t st)
 {
     if (!g_num_sms) {
         int dev = 0;
@@ -1236,11 +1237,11 @@ int launch_k(const EncodeParams &p, uint32_t max_wave_len, cudaStream_t st)
     }
     const size_t smem_multi = (size_t)(kEncMaxThreads * 13 + 1 + 2 * kEncMaxThreads + 33 + 3) * sizeof(uint32_t);
     if (max_wave_len > (uint32_t)kEncTileMaxL) {
-        encode_multi_kernel<K><<<p.nwaves, kEncMaxThreads, smem_multi, st>>>(p);
+        encode_multi_kernel<K><<<p.nwaves, kEncMaxThreads, smem_multi, st>>>(p, md.delta ? -1 : 0);
         return 1;
     }
     // large batches: one lane per wave (needs a worst-case sized scratch slot per wave)
-    if (p.lane_scratch && p.lane_slot_words) {
+    if (md.lane_scratch && md.lane_slot_words) {
         static bool attr_lane = false;
         const size_t smem_lane = (size_t)kLaneWarps * kLaneRingWords * 128;
         if (!attr_lane) {
@@ -1258,8 +1259,9 @@ int launch_k(const EncodeParams &p, uint32_t max_wave_len, cudaStream_t st)
         uint32_t grid = (uint32_t)(occ * g_num_sms);
         const uint32_t need = (ngroups + kLaneWarps - 1) / kLaneWarps;
         if (grid > need) grid = need;
-        encode_lane_kernel<K><<<grid, kLaneWarps * 32, smem_lane, st>>>(p, p.lane_scratch, p.lane_slot_words, ngroups, nslices,
-                                                                      p.lane_state, p.lane_slice_done);
+        encode_lane_kernel<K><<<grid, kLaneWarps * 32, smem_lane, st>>>(p, md.lane_scratch, md.lane_slot_words, ngroups, nslices,
+                                                                      md.lane_state, md.lane_slice_done,
+                                                                      md.delta ? 0xFFFF0001u : 1u, md.delta ? 0xFFFFFFFFu : 0u);
         return 1;
     }
     // per-warp staging (two buffers per worker warp): room for ~10 bits per sample, at most the
@@ -1291,18 +1293,20 @@ int launch_k(const EncodeParams &p, uint32_t max_wave_len, cudaStream_t st)
         if (grid > ntiles) grid = ntiles;
         kernel<<<grid, nthreads, smem, st>>>(p, stage, ntiles);
     };
-    static bool attr3 = false, attr2 = false;            // per K (this function is a template)
-    if (three) launch(encode_tile_kernel<K, 3>, attr3); else launch(encode_tile_kernel<K, 2>, attr2);
+    static bool attr3 = false, attr2 = false, attr2n = false;   // per K (this function is a template)
+    if (!md.delta) launch(encode_tile_kernel<K, 2, false>, attr2n);    // no delta (filter [1] / pre-filtered input)
+    else if (three) launch(encode_tile_kernel<K, 3, true>, attr3);
+    else launch(encode_tile_kernel<K, 2, true>, attr2);
     return 1;
 }
 
 }  // namespace
 
-int launch_encode(const EncodeParams &p, uint32_t max_wave_len, cudaStream_t st)
+int launch_encode(const EncodeParams &p, const EncodeMode &m, uint32_t max_wave_len, cudaStream_t st)
 {
     if (p.nwaves == 0) return 0;
     switch (p.k) {
-#define DRICE_CASE(K) case K: return launch_k<K>(p, max_wave_len, st);
+#define DRICE_CASE(K) case K: return launch_k<K>(p, m, max_wave_len, st);
         DRICE_CASE(0) DRICE_CASE(1) DRICE_CASE(2) DRICE_CASE(3) DRICE_CASE(4) DRICE_CASE(5)
         DRICE_CASE(6) DRICE_CASE(7) DRICE_CASE(8) DRICE_CASE(9) DRICE_CASE(10) DRICE_CASE(11)
         DRICE_CASE(12) DRICE_CASE(13) DRICE_CASE(14) DRICE_CASE(15)

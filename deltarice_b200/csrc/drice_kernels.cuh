@@ -42,10 +42,15 @@ struct EncodeParams {
     uint32_t        uniform_wpc;        // >0: every chunk has exactly this many waves
     uint32_t        L;                  // 0 = whole chunk is one wave
     int             k;
-    // pre-filter mode: delta (src/deltaRice.c:53-62) = (0xFFFF0001, 0xFFFFFFFF); none = (1, 0):
-    // the samples are Rice-coded as they are (filter [1], or already filtered by prefilter_kernel)
-    uint32_t        mul_x, neg_prev;
-    // lane-per-wave encoder (large batches): scratch of nwaves slots of lane_slot_words words
+};
+
+// what the encode launchers need beyond EncodeParams (kept out of it: the tile kernel's code
+// generation is sensitive to the size of its by-value parameter block)
+struct EncodeMode {
+    // pre-filter mode: 1 = delta (src/deltaRice.c:53-62), 0 = none: the samples are Rice-coded as
+    // they are (filter [1], or already filtered by prefilter_kernel)
+    int             delta;
+    // lane-per-wave encoder (large batches, opt-in): scratch of nwaves slots of lane_slot_words words
     // (worst case of a wave, multiple of 8); null = warp-per-wave tile kernel
     uint32_t       *lane_scratch;
     uint32_t        lane_slot_words;
@@ -94,7 +99,7 @@ struct ParseParams {
 };
 
 // launchers (drice_encode.cu / drice_decode.cu); return launches enqueued
-int launch_encode(const EncodeParams &p, uint32_t max_wave_len, cudaStream_t st);
+int launch_encode(const EncodeParams &p, const EncodeMode &m, uint32_t max_wave_len, cudaStream_t st);
 int launch_locate(const LocateParams &p, cudaStream_t st);
 int launch_parse(const ParseParams &p, int store_bytes, cudaStream_t st);
 // out[i] = sum_j in[i-j] * f[j] per wave (mod 2^16); in != out
