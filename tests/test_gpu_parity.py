@@ -263,3 +263,63 @@ def test_full_size_c2_roundtrip_and_sampled_parity(codec, oracle):
     # stream starts with its sample count
     heads = comp.view(torch.int32)[torch.from_numpy((boff[:-1] // 4).astype(np.int64)).cuda()]
     assert torch.equal(heads.cpu(), torch.from_numpy(np.diff(off).astype(np.int32)))
+
+
+@pytest.mark.parametrize("M", [1, 2, 4, 8, 16, 32, 64])
+def test_config_c3_rice_parameter_sweep(codec, oracle, M):
+    """BASELINE config C3 (RiceParameter sweep 1..64 at WaveformLength 7000): a 128 MiB slice per
+    parameter on the device path - round trip, the checksum-of-sizes property (stream bytes =
+    4*(chunks + waves + sum nwords)), and byte parity with the oracle on sampled chunks."""
+    import torch
+    from deltarice_b200 import chunk_offsets
+    from deltarice_b200.synth import nab_like_torch
+    n_waves, L, wpc = 9587, 7000, 2000
+    x = nab_like_torch(n_waves, L, 77 + M, "cuda").reshape(-1)
+    off = chunk_offsets(wpc * L, x.numel())
+    comp, boff = codec.encode_device(x, off, M, L)
+    y = codec.decode_device(comp, boff, off, M, L)
+    assert torch.equal(x, y)
+    words = comp.view(torch.int32)
+    total = 0
+    for c in (0, len(off) - 2):
+        xs = x[int(off[c]):int(off[c + 1])].cpu().numpy()
+        want = oracle.encode_chunk(xs, M, L, mt=True)
+        got = comp[int(boff[c]):int(boff[c + 1])].cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, want), (M, c)
+    # walk the headers of the whole stream on the host: sizes must add up exactly
+    w = words.cpu().numpy().view(np.uint32)
+    for c in range(len(off) - 1):
+        cur = int(boff[c]) // 4
+        assert w[cur] == int(off[c + 1] - off[c])
+        cur += 1
+        nw = -(-int(off[c + 1] - off[c]) // L)
+        for _ in range(nw):
+            cur += int(w[cur]) + 1
+        assert cur == int(boff[c + 1]) // 4, (M, c)
+        total += cur - int(boff[c]) // 4
+    assert total * 4 == comp.numel()
+
+
+def test_config_c4_mixed_noise_decode(codec, oracle):
+    """BASELINE config C4 (decode of a pre-compressed stream with mixed noise levels: long unary
+    runs next to escape-dominated waves in the same warp): 64 MiB slice, stream checked against the
+    oracle on sampled chunks, then decoded on the device and compared with the input."""
+    import torch
+    from deltarice_b200 import chunk_offsets
+    from deltarice_b200.synth import gaussian_mix
+    n_waves, L, M, wpc = 4794, 7000, 8, 600
+    xh = gaussian_mix(n_waves, L, seed=11).ravel()
+    x = torch.from_numpy(xh).cuda()
+    off = chunk_offsets(wpc * L, x.numel())
+    comp, boff = codec.encode_device(x, off, M, L)
+    for c in (0, 3, len(off) - 2):
+        want = oracle.encode_chunk(xh[int(off[c]):int(off[c + 1])], M, L, mt=True)
+        got = comp[int(boff[c]):int(boff[c + 1])].cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, want), c
+    y = codec.decode_device(comp, boff, off, M, L)
+    assert torch.equal(x, y)
+    # decode of the oracle's own stream for one chunk (not produced by our encoder)
+    c = 1
+    s = oracle.encode_chunk(xh[int(off[c]):int(off[c + 1])], M, L, mt=True)
+    back = codec.decode_host(s.view(np.uint8), None, None, M, L)
+    assert np.array_equal(back, xh[int(off[c]):int(off[c + 1])])
