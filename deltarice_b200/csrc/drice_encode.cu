@@ -59,14 +59,6 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
-// a * b + c with a 64-bit result: IMAD.WIDE.U32 (FMA pipe).  With b = 2^len this is
-// "shift a left by len inside a 64-bit window and append c".
-__device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c)
-{
-    uint64_t d;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
-    return d;
-}
 // 1 << s through PTX so the compiler keeps the multiply form of the appends
 __device__ __forceinline__ uint32_t pow2(uint32_t s)
 {
@@ -1302,17 +1294,62 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
 
 }  // namespace
 
-int launch_encode(const EncodeParams &p, const EncodeMode &m, uint32_t max_wave_len, cudaStream_t st)
-{
-    if (p.nwaves == 0) return 0;
-    switch (p.k) {
+// The 16 Rice parameters are instantiated in four translation units (the same source compiled with
+// DRICE_PART = 0..3, see the Makefile) so that the build parallelises; part 0 holds the dispatcher.
+#ifndef DRICE_PART
+#define DRICE_PART 0
+#define DRICE_SINGLE_TU 1
+#endif
+#define DRICE_CAT2(a, b) a##b
+#define DRICE_CAT(a, b) DRICE_CAT2(a, b)
+
+int launch_encode_part0(const EncodeParams &p, const EncodeMode &m, uint32_t max_wave_len, cudaStream_t st);
+int launch_encode_part1(const EncodeParams &p, const EncodeMode &m, uint32_t max_wave_len, cudaStream_t st);
+int launch_encode_part2(const EncodeParams &p, const EncodeMode &m, uint32_t max_wave_len, cudaStream_t st);
+int launch_encode_part3(const EncodeParams &p, const EncodeMode &m, uint32_t max_wave_len, cudaStream_t st);
+
 #define DRICE_CASE(K) case K: return launch_k<K>(p, m, max_wave_len, st);
+#ifdef DRICE_SINGLE_TU
+int launch_encode_part0(const EncodeParams &p, const EncodeMode &m, uint32_t max_wave_len, cudaStream_t st)
+{
+    switch (p.k) {
         DRICE_CASE(0) DRICE_CASE(1) DRICE_CASE(2) DRICE_CASE(3) DRICE_CASE(4) DRICE_CASE(5)
         DRICE_CASE(6) DRICE_CASE(7) DRICE_CASE(8) DRICE_CASE(9) DRICE_CASE(10) DRICE_CASE(11)
         DRICE_CASE(12) DRICE_CASE(13) DRICE_CASE(14) DRICE_CASE(15)
-#undef DRICE_CASE
     }
     return -1;
 }
+int launch_encode_part1(const EncodeParams &, const EncodeMode &, uint32_t, cudaStream_t) { return -1; }
+int launch_encode_part2(const EncodeParams &, const EncodeMode &, uint32_t, cudaStream_t) { return -1; }
+int launch_encode_part3(const EncodeParams &, const EncodeMode &, uint32_t, cudaStream_t) { return -1; }
+#else
+// part q holds K = 4q .. 4q+3
+int DRICE_CAT(launch_encode_part, DRICE_PART)(const EncodeParams &p, const EncodeMode &m, uint32_t max_wave_len, cudaStream_t st)
+{
+    switch (p.k) {
+        DRICE_CASE(4 * DRICE_PART) DRICE_CASE(4 * DRICE_PART + 1) DRICE_CASE(4 * DRICE_PART + 2) DRICE_CASE(4 * DRICE_PART + 3)
+    }
+    return -1;
+}
+#endif
+#undef DRICE_CASE
+
+#if DRICE_PART == 0
+int launch_encode(const EncodeParams &p, const EncodeMode &m, uint32_t max_wave_len, cudaStream_t st)
+{
+    if (p.nwaves == 0) return 0;
+    if (p.k < 0 || p.k > 15) return -1;
+#ifdef DRICE_SINGLE_TU
+    return launch_encode_part0(p, m, max_wave_len, st);
+#else
+    switch (p.k >> 2) {
+        case 0: return launch_encode_part0(p, m, max_wave_len, st);
+        case 1: return launch_encode_part1(p, m, max_wave_len, st);
+        case 2: return launch_encode_part2(p, m, max_wave_len, st);
+        default: return launch_encode_part3(p, m, max_wave_len, st);
+    }
+#endif
+}
+#endif
 
 }  // namespace drice
