@@ -57,6 +57,79 @@ def apply_filter(data: bytes, cd_values=(), reverse: bool = False) -> bytes:
     return out
 
 
+# --------------------------------------------------------------------------------------
+# direct-chunk batch front-end
+# --------------------------------------------------------------------------------------
+# libhdf5's filter pipeline hands the filter ONE chunk per call.  Writers / readers that own their
+# chunking bypass it (H5Dwrite_chunk / H5Dread_chunk, h5py write_direct_chunk / read_direct_chunk)
+# and push all the chunks of a dataset through the chunk scheduler in one call; the stored chunks
+# are exactly what the stock CPU filter would have produced, so the file stays readable without
+# this library.
+def chunk_grid(shape, chunks):
+    """Chunk origins of an HDF5 dataset of `shape` with chunk shape `chunks`, in the row-major
+    order libhdf5 enumerates them; edge chunks are full size (HDF5 pads them)."""
+    import itertools
+    import math
+    counts = [math.ceil(s / c) for s, c in zip(shape, chunks)]
+    return [tuple(i * c for i, c in zip(idx, chunks)) for idx in itertools.product(*[range(n) for n in counts])]
+
+
+def encode_dataset_chunks(codec, data, chunks, compression_opts=(), fill_value=0):
+    """Encodes every chunk of an int16 array in ONE batch call.  Returns [(origin, bytes)] ready
+    for `dset.id.write_direct_chunk(origin, bytes, filter_mask=0)`.  `compression_opts` is the
+    reference's tuple (RiceParameter, WaveformLength[, filter_len, taps...]); WaveformLength
+    counts samples of the flattened chunk, as in the filter."""
+    import numpy as np
+    from . import codec as _codec
+    data = np.asarray(data)
+    if data.dtype.itemsize != 2:
+        raise ValueError("Delta-Rice codes 16-bit samples")
+    M, L, taps = _codec.parse_cd_values_full(tuple(compression_opts))
+    origins = chunk_grid(data.shape, chunks)
+    n_per = int(np.prod(chunks))
+    flat = np.empty(len(origins) * n_per, dtype=np.int16)
+    for k, org in enumerate(origins):
+        block = np.full(chunks, fill_value, dtype=data.dtype)
+        src = tuple(slice(o, min(o + c, s)) for o, c, s in zip(org, chunks, data.shape))
+        dst = tuple(slice(0, sl.stop - sl.start) for sl in src)
+        block[dst] = data[src]
+        flat[k * n_per:(k + 1) * n_per] = block.view(np.int16).ravel()
+    off = np.arange(len(origins) + 1, dtype=np.uint64) * n_per
+    codec.set_filter(None if taps == (1, -1) else taps)
+    try:
+        stream, boff = codec.encode_host(flat, off, M, None if L < 0 else L)
+    finally:
+        codec.set_filter(None)
+    return [(org, stream[int(boff[k]):int(boff[k + 1])].tobytes()) for k, org in enumerate(origins)]
+
+
+def decode_dataset_chunks(codec, chunk_bytes, shape, chunks, compression_opts=(), dtype="int16"):
+    """Inverse of encode_dataset_chunks: `chunk_bytes` = the stored chunks in chunk_grid order
+    (e.g. from `dset.id.read_direct_chunk(origin)[1]`); returns the array of `shape`."""
+    import numpy as np
+    from . import codec as _codec
+    M, L, taps = _codec.parse_cd_values_full(tuple(compression_opts))
+    origins = chunk_grid(shape, chunks)
+    if len(chunk_bytes) != len(origins):
+        raise ValueError("one stored chunk per grid cell expected")
+    n_per = int(np.prod(chunks))
+    comp = np.frombuffer(b"".join(chunk_bytes), dtype=np.uint8)
+    boff = np.concatenate([[0], np.cumsum([len(b) for b in chunk_bytes])]).astype(np.uint64)
+    off = np.arange(len(origins) + 1, dtype=np.uint64) * n_per
+    codec.set_filter(None if taps == (1, -1) else taps)
+    try:
+        flat = codec.decode_host(comp, boff, off, M, None if L < 0 else L)
+    finally:
+        codec.set_filter(None)
+    out = np.empty(shape, dtype=np.dtype(dtype))
+    for k, org in enumerate(origins):
+        block = flat[k * n_per:(k + 1) * n_per].view(out.dtype).reshape(chunks)
+        dst = tuple(slice(o, min(o + c, s)) for o, c, s in zip(org, chunks, shape))
+        src = tuple(slice(0, sl.stop - sl.start) for sl in dst)
+        out[dst] = block[src]
+    return out
+
+
 def _auto_register():
     try:
         import h5py  # noqa: F401

@@ -323,3 +323,30 @@ def test_config_c4_mixed_noise_decode(codec, oracle):
     s = oracle.encode_chunk(xh[int(off[c]):int(off[c + 1])], M, L, mt=True)
     back = codec.decode_host(s.view(np.uint8), None, None, M, L)
     assert np.array_equal(back, xh[int(off[c]):int(off[c + 1])])
+
+
+def test_direct_chunk_batch_front_end(codec, oracle):
+    """all chunks of a dataset through ONE batch call; every stored chunk must be
+    what the filter produces for that chunk (README config: (100,7000) int16, chunks (20,7000),
+    opts (8, 7000)), edge chunks padded as HDF5 pads them, generic opts included."""
+    from deltarice_b200 import h5
+    data = np.random.default_rng(0).normal(0, 10, (100, 7000)).astype(np.int16)
+    stored = h5.encode_dataset_chunks(codec, data, (20, 7000), (8, 7000))
+    assert [o for o, _ in stored] == [(i, 0) for i in range(0, 100, 20)]
+    for (org, b) in stored:
+        want = oracle.encode_chunk(data[org[0]:org[0] + 20].ravel(), 8, 7000)
+        assert np.array_equal(np.frombuffer(b, np.uint32), want)
+        assert b == h5.apply_filter(data[org[0]:org[0] + 20].tobytes(), (8, 7000))
+    back = h5.decode_dataset_chunks(codec, [b for _, b in stored], data.shape, (20, 7000), (8, 7000))
+    assert np.array_equal(back, data)
+    # ragged grid (edge chunks padded with the fill value) and an option tuple with a pre-filter
+    d2 = np.random.default_rng(1).integers(-3000, 3000, (50, 333)).astype(np.int16)
+    opts = (4, 0xFFFFFFFF, 3, 1, 0xFFFFFFFE, 1)
+    stored = h5.encode_dataset_chunks(codec, d2, (16, 128), opts)
+    assert len(stored) == 4 * 3
+    org, b = stored[-1]
+    block = np.zeros((16, 128), np.int16)
+    block[:50 - org[0], :333 - org[1]] = d2[org[0]:, org[1]:]
+    assert np.array_equal(np.frombuffer(b, np.uint32), oracle.encode_chunk(block.ravel(), 4, None, filt=[1, -2, 1]))
+    back = h5.decode_dataset_chunks(codec, [bb for _, bb in stored], d2.shape, (16, 128), opts)
+    assert np.array_equal(back, d2)
