@@ -64,6 +64,7 @@ struct drice_ctx {
     int filter[drice::kMaxFilter] = {1, -1};
     DevBuf d_filt;                       // generic filter: pre-filtered samples of the batch
     DevBuf d_lane;                       // lane-per-wave encoder: one worst-case slot per wave
+    DevBuf d_scan;                       // locate by scanning: per-tile header candidates
 
     // optional per-kernel timing (drice_timing_*): event pairs recorded around launches
     bool timing = false;
@@ -381,7 +382,7 @@ extern "C" void drice_destroy(drice_ctx *ctx)
     }
     for (auto &t : ctx->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
-    ctx->d_tab.release(); ctx->d_scratch.release(); ctx->d_offs.release(); ctx->d_filt.release(); ctx->d_lane.release();
+    ctx->d_tab.release(); ctx->d_scratch.release(); ctx->d_offs.release(); ctx->d_filt.release(); ctx->d_lane.release(); ctx->d_scan.release();
     if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
     if (ctx->h_sync) cudaFreeHost(ctx->h_sync);
     if (ctx->ev_tab) cudaEventDestroy(ctx->ev_tab);
@@ -652,8 +653,16 @@ extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_co
     lp.nchunks = (uint32_t)nchunks;
     lp.L = g.Lk;
     {
+        uint64_t max_chunk_words = 0;
+        for (size_t c = 0; c < nchunks; ++c) max_chunk_words = std::max<uint64_t>(max_chunk_words, woff[c + 1] - woff[c]);
+        size_t scan_bytes = 0;
+        const bool scan = locate_scan_applies(g.Lk, k, max_chunk_words, nchunks, &scan_bytes);
+        if (scan) {
+            if (scan_bytes > ctx->d_scan.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
+            DR_CUDA(ctx, ctx->d_scan.reserve(scan_bytes));
+        }
         TimedScope ts(ctx, DRICE_KERNEL_LOCATE, st);
-        ctx->launches += (uint64_t)launch_locate(lp, st);
+        ctx->launches += (uint64_t)(scan ? launch_locate_scan(lp, k, max_chunk_words, ctx->d_scan.p, st) : launch_locate(lp, st));
     }
 
     ParseParams pp{};

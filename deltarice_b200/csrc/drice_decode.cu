@@ -296,6 +296,208 @@ __global__ void __launch_bounds__(kLocThreads) locate_kernel(const LocateParams 
 }
 
 // ------------------------------------------------------------------------------------
+// locate by scanning (waves of a few thousand samples: the benchmark case)
+// ------------------------------------------------------------------------------------
+// A record header is the word count of a wave of n samples: ceil(n (k+1) / 32) <= nwords <=
+// ceil(25 n / 32).  Code words practically never fall in that range (zero runs inside the codes are
+// at most k + 12 bits long, so a code word is >= 2^(19-k), far above any header of a wave shorter
+// than a million samples), so the headers can be FOUND instead of chased: every SM streams part of
+// the batch (scan_headers_kernel: 16 KB tiles, candidates = words in range whose record would end
+// inside the chunk, kept in position order per tile), then one CTA per chunk ranks the tiles'
+// candidates, fills the wave table and VERIFIES it - the table is right if and only if it starts
+// at the chunk's first record, has exactly the expected number of entries and every entry + its
+// word count + 1 is the next entry (the last one: the chunk's end).  If anything is off (a false
+// candidate, a malformed stream) that chunk falls back to the exact serial chase through global
+// memory, which also produces the error status.  The chase's one-SM-per-chunk streaming limit
+// (33 GB/s per SM) is gone: the scan runs at HBM speed on all SMs.
+constexpr int kScanTileWords = 4096;          // 16 KB per CTA
+constexpr int kScanThreads   = 128;           // 32 words per thread
+constexpr int kScanCap       = 64;            // candidates a tile can hold
+
+struct ScanParams {
+    LocateParams lp;
+    uint32_t    *cnt;                         // [nchunks * max_tiles] candidates per tile (0xFFFFFFFF: overflow)
+    uint32_t    *cand;                        // [nchunks * max_tiles * kScanCap] positions relative to the chunk's first word
+    uint32_t     max_tiles;                   // tiles per chunk (stride of the two arrays)
+    int          k;
+};
+
+struct ChunkGeom {
+    uint64_t wb, we, sb, total, Lw;
+    uint32_t g0, W, lo, hi;
+    int64_t  A0;
+};
+__device__ __forceinline__ ChunkGeom chunk_geom(const LocateParams &p, uint32_t c, int k)
+{
+    ChunkGeom g;
+    g.wb = p.chunk_word_off[c];
+    g.we = p.chunk_word_off[c + 1];
+    g.sb = p.chunk_sample_off[c];
+    g.total = p.chunk_sample_off[c + 1] - g.sb;
+    g.g0 = p.chunk_wave_off[c];
+    g.W = p.chunk_wave_off[c + 1] - g.g0;
+    g.Lw = p.L ? (uint64_t)p.L : g.total;
+    const uint64_t n_last = g.W ? g.total - (uint64_t)(g.W - 1) * g.Lw : 0;
+    const uint64_t n_min = n_last < g.Lw ? n_last : g.Lw;
+    const uint64_t lo = (n_min * (uint64_t)(k + 1) + 31) / 32;
+    g.lo = (uint32_t)(lo ? lo : 1);
+    g.hi = (uint32_t)((25ull * g.Lw + 31) / 32);
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(p.comp) >> 2) & 3u);
+    g.A0 = (int64_t)((g.wb + 1 + mis) & ~3ull) - (int64_t)mis;     // 16-byte aligned address at or below the first record
+    return g;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_headers_kernel(const ScanParams sp)
+{
+    __shared__ uint32_t s_n;
+    __shared__ uint32_t s_list[kScanCap];
+    const LocateParams &p = sp.lp;
+    const uint32_t c = blockIdx.y, t = blockIdx.x;
+    const ChunkGeom g = chunk_geom(p, c, sp.k);
+    const size_t slot = (size_t)c * sp.max_tiles + t;
+    const int64_t t0 = g.A0 + (int64_t)t * kScanTileWords;
+    if (g.we <= g.wb + 1 || t0 >= (int64_t)g.we) {
+        if (threadIdx.x == 0) sp.cnt[slot] = 0;
+        return;
+    }
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const uint32_t span = g.hi - g.lo;
+#pragma unroll
+    for (int r = 0; r < kScanTileWords / 4 / kScanThreads; ++r) {
+        const int64_t b = t0 + 4ll * (r * kScanThreads + (int)threadIdx.x);
+        if (b >= (int64_t)g.we || b + 4 <= (int64_t)g.wb + 1) continue;
+        uint32_t x[4];
+        if (b >= 0 && (uint64_t)b + 4 <= p.comp_words) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p.comp + b));
+            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = (b + e >= 0 && (uint64_t)(b + e) < p.comp_words) ? p.comp[b + e] : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t i = b + e;
+            if (i > (int64_t)g.wb && i < (int64_t)g.we && x[e] - g.lo <= span && (uint64_t)i + 1 + x[e] <= g.we) {
+                const uint32_t at = atomicAdd(&s_n, 1u);
+                if (at < (uint32_t)kScanCap) s_list[at] = (uint32_t)((uint64_t)i - g.wb);
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t n = s_n;
+    if (n > (uint32_t)kScanCap) {
+        if (threadIdx.x == 0) sp.cnt[slot] = 0xFFFFFFFFu;
+        return;
+    }
+    if (threadIdx.x < n) {                               // position order: rank by counting (n <= 64)
+        const uint32_t mine = s_list[threadIdx.x];
+        uint32_t rank = 0;
+        for (uint32_t m = 0; m < n; ++m) rank += s_list[m] < mine;
+        sp.cand[slot * kScanCap + rank] = mine;
+    }
+    if (threadIdx.x == 0) sp.cnt[slot] = n;
+}
+
+constexpr int kRankThreads = 256;
+
+__global__ void __launch_bounds__(kRankThreads) rank_headers_kernel(const ScanParams sp)
+{
+    __shared__ uint32_t s_warp[kRankThreads / 32];
+    __shared__ uint32_t s_base, s_bad, s_located;
+    const LocateParams &p = sp.lp;
+    const uint32_t c = blockIdx.x;
+    const ChunkGeom g = chunk_geom(p, c, sp.k);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (g.we <= g.wb) {                                  // no stream at all
+        if (threadIdx.x == 0) atomicOr(p.status, kErrStream);
+        for (uint32_t w = threadIdx.x; w < g.W; w += kRankThreads) { p.wave_in[g.g0 + w] = g.wb; p.wave_out[g.g0 + w] = g.sb; p.wave_n[g.g0 + w] = 0; }
+        return;
+    }
+    if (g.W == 0) {
+        if (threadIdx.x == 0) {
+            if (p.comp[g.wb] != (uint32_t)g.total) atomicOr(p.status, kErrTotal);
+            if (g.we != g.wb + 1) atomicOr(p.status, kErrStream);
+        }
+        return;
+    }
+    if (threadIdx.x == 0) {
+        s_base = 0;
+        s_bad = 0;
+        s_located = g.W;
+        if (p.comp[g.wb] != (uint32_t)g.total) atomicOr(p.status, kErrTotal);
+    }
+    // the chain-independent part of the wave table
+    for (uint32_t w = threadIdx.x; w < g.W; w += kRankThreads) {
+        const uint64_t s0 = (uint64_t)w * g.Lw;
+        p.wave_out[g.g0 + w] = g.sb + s0;
+        p.wave_n[g.g0 + w] = (uint32_t)((g.total - s0) < g.Lw ? (g.total - s0) : g.Lw);
+    }
+    __syncthreads();
+    // ---- rank: exclusive scan of the tiles' candidate counts, scatter in position order -----------
+    const uint32_t ntiles = (uint32_t)(((int64_t)g.we - g.A0 + kScanTileWords - 1) / kScanTileWords);
+    const size_t slot0 = (size_t)c * sp.max_tiles;
+    for (uint32_t tb = 0; tb < ntiles; tb += kRankThreads) {
+        const uint32_t t = tb + threadIdx.x;
+        uint32_t n = t < ntiles ? sp.cnt[slot0 + t] : 0u;
+        if (n == 0xFFFFFFFFu) { s_bad = 1; n = 0; }
+        uint32_t inc = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += u;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t woff = 0, btot = 0;
+#pragma unroll
+        for (int w = 0; w < kRankThreads / 32; ++w) {
+            if (w < warp) woff += s_warp[w];
+            btot += s_warp[w];
+        }
+        const uint32_t first = s_base + woff + inc - n;  // wave index of the tile's first candidate
+        for (uint32_t s2 = 0; s2 < n; ++s2) {
+            const uint32_t w = first + s2;
+            if (w < g.W) p.wave_in[g.g0 + w] = g.wb + sp.cand[(slot0 + t) * kScanCap + s2];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += btot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && s_base != g.W) s_bad = 1;
+    __threadfence_block();
+    __syncthreads();
+    // ---- verify: the table is the chain cur += word[cur] + 1 (src/deltaRice.c:319-325) ------------
+    if (!s_bad) {
+        bool bad = false;
+        for (uint32_t w = threadIdx.x; w < g.W; w += kRankThreads) {
+            const uint64_t pos = p.wave_in[g.g0 + w];
+            const uint64_t nxt = (w + 1 < g.W) ? p.wave_in[g.g0 + w + 1] : g.we;
+            bad |= (pos + 1 + (uint64_t)p.comp[pos] != nxt) || (w == 0 && pos != g.wb + 1);
+        }
+        if (bad) s_bad = 1;
+    }
+    __syncthreads();
+    if (s_bad) {
+        // ---- fallback: the exact serial chase through global memory (also finds stream errors) ----
+        if (threadIdx.x == 0) {
+            uint64_t cur = g.wb + 1;
+            uint32_t w = 0;
+            while (w < g.W && cur < g.we) {
+                p.wave_in[g.g0 + w] = cur;
+                cur += (uint64_t)__ldg(p.comp + cur) + 1ull;
+                ++w;
+            }
+            if (w < g.W) s_located = w;
+            if (w < g.W || cur != g.we) atomicOr(p.status, kErrStream);
+        }
+        __syncthreads();
+        for (uint32_t x = s_located + threadIdx.x; x < g.W; x += kRankThreads) { p.wave_in[g.g0 + x] = g.wb; p.wave_out[g.g0 + x] = g.sb; p.wave_n[g.g0 + x] = 0; }
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // parse
 // ------------------------------------------------------------------------------------
 // Rice parsing is a serial chain per wave (a code's length is only known once its unary
@@ -728,6 +930,50 @@ int launch_locate(const LocateParams &p, cudaStream_t st)
     }
     locate_kernel<<<p.nchunks, kLocThreads, smem, st>>>(p);
     return 1;
+}
+
+// scan + rank instead of the chase: when the waves are long enough for a tile to hold all its
+// headers (and short enough for the scan to make sense).  `max_chunk_words`: longest chunk stream.
+bool locate_scan_applies(uint32_t L, int k, uint64_t max_chunk_words, size_t nchunks, size_t *scratch_bytes)
+{
+    static int mode = -1;                                // DRICE_LOCATE_SCAN=0 forces the chase
+    if (mode < 0) {
+        const char *e = getenv("DRICE_LOCATE_SCAN");
+        mode = e ? atoi(e) : 1;
+    }
+    if (!mode || L == 0 || (uint64_t)L >= kLocDirectL || k < 0) return false;
+    const uint64_t lo_full = ((uint64_t)L * (uint64_t)(k + 1) + 31) / 32;
+    if ((lo_full + 1) * (uint64_t)(kScanCap - 2) < (uint64_t)kScanTileWords) return false;
+    const uint64_t max_tiles = (max_chunk_words + 3) / kScanTileWords + 2;
+    const uint64_t bytes = (uint64_t)nchunks * max_tiles * (kScanCap + 1) * 4;
+    if (max_tiles > 65535 || nchunks > 0x7fffffffull || bytes > (512ull << 20)) return false;
+    *scratch_bytes = (size_t)bytes;
+    return true;
+}
+
+int launch_locate_scan(const LocateParams &p, int k, uint64_t max_chunk_words, void *scratch, cudaStream_t st)
+{
+    if (p.nchunks == 0) return 0;
+    ScanParams sp;
+    sp.lp = p;
+    sp.k = k;
+    sp.max_tiles = (uint32_t)((max_chunk_words + 3) / kScanTileWords + 2);
+    sp.cnt = (uint32_t *)scratch;
+    sp.cand = sp.cnt + (size_t)p.nchunks * sp.max_tiles;
+    // (y = chunk: grids of more than 65535 chunks go in slices)
+    for (uint32_t c0 = 0; c0 < p.nchunks; c0 += 65535u) {
+        ScanParams q = sp;
+        const uint32_t nc = p.nchunks - c0 < 65535u ? p.nchunks - c0 : 65535u;
+        q.lp.chunk_word_off += c0;
+        q.lp.chunk_sample_off += c0;
+        q.lp.chunk_wave_off += c0;
+        q.lp.nchunks = nc;
+        q.cnt += (size_t)c0 * sp.max_tiles;
+        q.cand += (size_t)c0 * sp.max_tiles * kScanCap;
+        scan_headers_kernel<<<dim3(sp.max_tiles, nc), kScanThreads, 0, st>>>(q);
+    }
+    rank_headers_kernel<<<p.nchunks, kRankThreads, 0, st>>>(sp);
+    return 2;
 }
 
 int launch_parse(const ParseParams &p, int store_bytes, cudaStream_t st)

@@ -101,6 +101,9 @@ struct ParseParams {
 // launchers (drice_encode.cu / drice_decode.cu); return launches enqueued
 int launch_encode(const EncodeParams &p, const EncodeMode &m, uint32_t max_wave_len, cudaStream_t st);
 int launch_locate(const LocateParams &p, cudaStream_t st);
+// header scan instead of the chase (drice_decode.cu): applicability + scratch size, launcher
+bool locate_scan_applies(uint32_t L, int k, uint64_t max_chunk_words, size_t nchunks, size_t *scratch_bytes);
+int launch_locate_scan(const LocateParams &p, int k, uint64_t max_chunk_words, void *scratch, cudaStream_t st);
 int launch_parse(const ParseParams &p, int store_bytes, cudaStream_t st);
 // out[i] = sum_j in[i-j] * f[j] per wave (mod 2^16); in != out
 int launch_prefilter(const FilterParams &p, const int16_t *in, int16_t *out, uint64_t max_chunk_samples, cudaStream_t st);
