@@ -350,3 +350,28 @@ def test_direct_chunk_batch_front_end(codec, oracle):
     assert np.array_equal(np.frombuffer(b, np.uint32), oracle.encode_chunk(block.ravel(), 4, None, filt=[1, -2, 1]))
     back = h5.decode_dataset_chunks(codec, [bb for _, bb in stored], d2.shape, (16, 128), opts)
     assert np.array_equal(back, d2)
+
+
+def test_more_than_65535_chunks(codec, oracle):
+    """Grids are sliced at 65535 chunks in y (header scan, pre-filter): 70 000 one-wave chunks of
+    4096 samples on the device path, with and without a pre-filter; sampled chunks against the oracle."""
+    import torch
+    from deltarice_b200 import chunk_offsets
+    n_chunks, n, M = 70000, 4096, 4
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    x = (torch.randn(n_chunks * n, generator=g, device="cuda") * 6).cumsum(0).remainder(4000).to(torch.int16)
+    off = chunk_offsets(n, x.numel())
+    for taps in (None, [1, -2, 1]):
+        codec.set_filter(taps)
+        try:
+            comp, boff = codec.encode_device(x, off, M, n)
+            y = codec.decode_device(comp, boff, off, M, n)
+        finally:
+            codec.set_filter(None)
+        assert torch.equal(x, y), taps
+        for c in (0, 65534, 65535, 65536, n_chunks - 1):
+            xs = x[int(off[c]):int(off[c + 1])].cpu().numpy()
+            want = oracle.encode_chunk(xs, M, n, filt=taps)
+            got = comp[int(boff[c]):int(boff[c + 1])].cpu().numpy().view(np.uint32)
+            assert np.array_equal(got, want), (taps, c)
