@@ -838,6 +838,158 @@ __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const Par
     }
 }
 
+// ------------------------------------------------------------------------------------
+// parse, small batches: one CTA per wave, parallel INSIDE the wave
+// ------------------------------------------------------------------------------------
+// A Rice stream is a serial chain (a code's position is the end of the previous one), so with
+// one lane per wave a single HDF5 chunk of 20 waves is 20 lanes each walking 7000 codes: 0.7 ms,
+// three times slower than the reference on a CPU.  For batches too small to fill the machine with
+// lanes the chain is broken up instead: cut the record into runs of four words.  The bit offset at
+// which the first code of a run starts (0..24: a code is at most 25 bits) determines where the
+// first code of the NEXT run starts - a transition function with 25 inputs.  A warp evaluates the
+// function of a run for all entry offsets at once (lane o decodes the run speculatively from offset
+// o), the functions are composed along the record (a chain of one shared-memory lookup per run
+// instead of one table lookup per code), and then every run is decoded independently from its now
+// known entry: counts and delta sums first, a block scan for the sample indices and the inverse
+// delta's running values, then the samples.  32x redundant table lookups, but spread over 512
+// threads and a few SMs that would otherwise idle.
+constexpr int kWideThreads  = 512;
+constexpr int kWideRunWords = 4;                         // 128 bits per run
+constexpr int kWideMaxWords = 6400;                      // ceil(25 * 8192 / 32): waves up to 8192 samples
+constexpr int kWideMaxRuns  = kWideMaxWords / kWideRunWords;
+constexpr uint32_t kWideMaxWaves = 4096;                 // beyond that one lane per wave fills the machine
+constexpr int kWideLutBits  = 12;
+
+struct WideCode { uint32_t len; int delta; bool valid; };
+// the code at bit `pos` of the record in shared memory (words padded with two zero words)
+__device__ __forceinline__ WideCode wide_decode_at(const uint32_t *words, const uint32_t *lut, uint32_t pos, int k, uint32_t kmask)
+{
+    const uint32_t w = pos >> 5;
+    const uint32_t win = __funnelshift_l(words[w + 1], words[w], pos);
+    const uint32_t e = lut[win >> (32 - kWideLutBits)];
+    WideCode c;
+    if (e) {
+        c.len = e & 31u;
+        c.delta = (int)e >> 16;
+        c.valid = true;
+        return c;
+    }
+    const uint32_t q = __clz(win);
+    uint32_t u;
+    c.valid = true;
+    if (q == kEscapeQuotient) {
+        u = (win >> 7) & 0xFFFFu;
+        c.len = kEscapeBits;
+    } else if (q < kEscapeQuotient) {
+        c.len = q + 1 + (uint32_t)k;
+        u = (q << k) | ((win >> (32u - c.len)) & kmask);
+    } else {                                             // not a code (junk offset, padding, malformed stream)
+        u = 0;
+        c.len = 1;
+        c.valid = false;
+    }
+    const uint32_t h = u >> 1;
+    c.delta = (int)((u & 1u) ? ~h : h);
+    return c;
+}
+
+template <bool IDENT>
+__global__ void __launch_bounds__(kWideThreads, 2) parse_wide_kernel(const ParseParams p)
+{
+    extern __shared__ __align__(16) uint32_t wsm[];
+    uint32_t *words = wsm;                                       // kWideMaxWords + 2
+    uint32_t *lut = words + kWideMaxWords + 2;                   // 4096
+    uint32_t *cnt = lut + (1 << kWideLutBits);                   // per thread: codes / delta sum of its runs
+    uint32_t *dsum = cnt + kWideThreads;
+    uint8_t *T = reinterpret_cast<uint8_t *>(dsum + kWideThreads);   // [kWideMaxRuns][32] transition functions
+    uint8_t *E = T + kWideMaxRuns * 32;                          // [kWideMaxRuns + 1] entry offsets
+    __shared__ uint32_t s_warp_c[kWideThreads / 32], s_warp_d[kWideThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k = p.k;
+    const uint32_t kmask = (1u << k) - 1u;
+    for (uint32_t i = threadIdx.x; i < (1u << kWideLutBits); i += kWideThreads) lut[i] = make_lut_entry(i, k, kWideLutBits);
+
+    for (uint32_t g = blockIdx.x; g < p.nwaves; g += gridDim.x) {
+        __syncthreads();                                         // (previous wave done with shared memory; LUT built)
+        const uint32_t n = p.wave_n[g];
+        if (n == 0) continue;
+        const uint64_t rec = p.wave_in[g];
+        const uint32_t nw = p.comp[rec];
+        int16_t *out = p.out + p.wave_out[g];
+        if (nw == 0 || nw > (uint32_t)kWideMaxWords || rec + 1 + nw > p.comp_words) {
+            if (threadIdx.x == 0) atomicOr(p.status, kErrStream);
+            continue;
+        }
+        for (uint32_t i = threadIdx.x; i < nw + 2; i += kWideThreads) words[i] = i < nw ? p.comp[rec + 1 + i] : 0u;
+        __syncthreads();
+        const uint32_t nruns = (nw + kWideRunWords - 1) / kWideRunWords;
+        // ---- transition function of every run: lane o enters at bit offset o ---------------------
+        for (uint32_t r = warp; r < nruns; r += kWideThreads / 32) {
+            const uint32_t end = (r + 1) * (kWideRunWords * 32);
+            uint32_t pos = r * (kWideRunWords * 32) + (uint32_t)lane;
+            while (pos < end) pos += wide_decode_at(words, lut, pos, k, kmask).len;
+            T[r * 32 + lane] = (uint8_t)(pos - end);             // < 25
+        }
+        __syncthreads();
+        // ---- entry offset of every run: compose along the record --------------------------------
+        if (threadIdx.x == 0) {
+            uint32_t e = 0;
+            for (uint32_t r = 0; r < nruns; ++r) {
+                E[r] = (uint8_t)e;
+                e = T[r * 32 + e];
+            }
+        }
+        __syncthreads();
+        // ---- every thread takes consecutive runs: codes and delta sum first ---------------------
+        const uint32_t rpt = (nruns + kWideThreads - 1) / kWideThreads;
+        const uint32_t r0 = threadIdx.x * rpt, r1 = min(r0 + rpt, nruns);
+        uint32_t c = 0, dsm = 0;
+        for (uint32_t r = r0; r < r1; ++r) {
+            const uint32_t end = (r + 1) * (kWideRunWords * 32);
+            uint32_t pos = r * (kWideRunWords * 32) + E[r];
+            while (pos < end) {
+                const WideCode cd = wide_decode_at(words, lut, pos, k, kmask);
+                pos += cd.len;
+                ++c;
+                dsm += (uint32_t)cd.delta;
+            }
+        }
+        // block exclusive scan of (c, dsm)
+        uint32_t ic = c, id = dsm;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t tc = __shfl_up_sync(0xffffffffu, ic, d), td = __shfl_up_sync(0xffffffffu, id, d);
+            if (lane >= d) { ic += tc; id += td; }
+        }
+        if (lane == 31) { s_warp_c[warp] = ic; s_warp_d[warp] = id; }
+        __syncthreads();
+        uint32_t bc = 0, bd = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kWideThreads / 32; ++w) {
+            if (w < warp) { bc += s_warp_c[w]; bd += s_warp_d[w]; }
+            total += s_warp_c[w];
+        }
+        uint32_t idx = bc + ic - c;                              // sample index of the thread's first code
+        uint32_t acc = bd + id - dsm;                            // running sample before it (src/deltaRice.c:84-89)
+        bool bad = (threadIdx.x == 0 && total < n);
+        // ---- the samples --------------------------------------------------------------------------
+        for (uint32_t r = r0; r < r1 && idx < n; ++r) {
+            const uint32_t end = (r + 1) * (kWideRunWords * 32);
+            uint32_t pos = r * (kWideRunWords * 32) + E[r];
+            while (pos < end && idx < n) {
+                const WideCode cd = wide_decode_at(words, lut, pos, k, kmask);
+                pos += cd.len;
+                acc += (uint32_t)cd.delta;
+                bad |= !cd.valid;
+                out[idx] = (int16_t)(IDENT ? (uint32_t)cd.delta : acc);
+                ++idx;
+                if (idx == n) bad |= ((pos + 31u) >> 5) != nw;   // the codes must end inside the last word
+            }
+        }
+        if (bad) atomicOr(p.status, kErrStream);
+    }
+}
+
 int g_dec_sms = 0;
 
 // warps per SM: as many as fit, trimmed so that the last round of warp tasks is nearly full
@@ -873,6 +1025,28 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
         cudaFuncSetAttribute(parse_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
         cudaFuncSetAttribute(parse_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         attr_set = true;
+    }
+    // small batches: one CTA per wave (parallel inside the wave) instead of one lane per wave
+    {
+        static int wide = -1;                                // DRICE_PARSE_WIDE=0: always one lane per wave
+        if (wide < 0) {
+            const char *e = getenv("DRICE_PARSE_WIDE");
+            wide = e ? atoi(e) : 1;
+        }
+        if (wide && p.nwaves <= kWideMaxWaves && p.max_n <= 8192u) {
+            static bool wattr = false;
+            const size_t wsmem = (size_t)(kWideMaxWords + 2 + (1 << kWideLutBits) + 2 * kWideThreads) * 4 +
+                                 (size_t)kWideMaxRuns * 32 + kWideMaxRuns + 16;
+            if (!wattr) {
+                cudaFuncSetAttribute(parse_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+                cudaFuncSetAttribute(parse_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+                wattr = true;
+            }
+            const uint32_t wgrid = p.nwaves < (uint32_t)(2 * g_dec_sms) ? p.nwaves : (uint32_t)(2 * g_dec_sms);
+            if (p.identity) parse_wide_kernel<true><<<wgrid, kWideThreads, wsmem, st>>>(p);
+            else            parse_wide_kernel<false><<<wgrid, kWideThreads, wsmem, st>>>(p);
+            return 1;
+        }
     }
     const uint32_t ngroups = (p.nwaves + 31u) / 32u;
     static int max_warps = 0;

@@ -146,6 +146,24 @@ def test_lane_encoder_on_the_small_cases():
     assert " passed" in r.stdout
 
 
+def test_lane_parser_on_the_small_cases():
+    """Batches of up to 4096 waves (<= 8192 samples each) are decoded by parse_wide_kernel (one CTA
+    per wave, parallel inside the wave), larger ones by parse_kernel (one lane per wave).
+    DRICE_PARSE_WIDE=0 (read once per process) sends EVERY batch to the lane kernel: the edge-case
+    suite must stay exact there too."""
+    import subprocess
+    import sys
+    if os.environ.get("DRICE_PARSE_WIDE"):
+        pytest.skip("already running under the override")
+    env = dict(os.environ, DRICE_PARSE_WIDE="0")
+    sel = ("single_chunk_host_path or single_chunk_h5z_filter or golden or ragged_batch or generic_filter_batch "
+           "or unaligned_pointers or many_chunks or readme_config or errors")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", sel],
+                       env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout
+
+
 def test_readme_config_c1_batch(codec, oracle):
     """C1: (100,7000) N(0,10), M=8, chunks (20,7000): 5 chunks in ONE launch."""
     x = np.random.default_rng(0).normal(0, 10, (100, 7000)).astype(np.int16).ravel()
