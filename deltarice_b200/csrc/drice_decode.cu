@@ -857,7 +857,7 @@ constexpr int kWideThreads  = 512;
 constexpr int kWideRunWords = 4;                         // 128 bits per run
 constexpr int kWideMaxWords = 6400;                      // ceil(25 * 8192 / 32): waves up to 8192 samples
 constexpr int kWideMaxRuns  = kWideMaxWords / kWideRunWords;
-constexpr uint32_t kWideMaxWaves = 4096;                 // beyond that one lane per wave fills the machine
+constexpr uint32_t kWideMaxWaves = 896;                  // measured crossover with one lane per wave: ~900 (L = 3500) .. ~1100 (L = 7000) waves
 constexpr int kWideLutBits  = 12;
 
 struct WideCode { uint32_t len; int delta; bool valid; };
@@ -1028,12 +1028,12 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
     }
     // small batches: one CTA per wave (parallel inside the wave) instead of one lane per wave
     {
-        static int wide = -1;                                // DRICE_PARSE_WIDE=0: always one lane per wave
+        static long wide = -1;                               // DRICE_PARSE_WIDE=<max waves> (0: always one lane per wave)
         if (wide < 0) {
             const char *e = getenv("DRICE_PARSE_WIDE");
-            wide = e ? atoi(e) : 1;
+            wide = e ? atol(e) : (long)kWideMaxWaves;
         }
-        if (wide && p.nwaves <= kWideMaxWaves && p.max_n <= 8192u) {
+        if ((long)p.nwaves <= wide && p.max_n <= 8192u) {
             static bool wattr = false;
             const size_t wsmem = (size_t)(kWideMaxWords + 2 + (1 << kWideLutBits) + 2 * kWideThreads) * 4 +
                                  (size_t)kWideMaxRuns * 32 + kWideMaxRuns + 16;

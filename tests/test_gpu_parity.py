@@ -147,7 +147,7 @@ def test_lane_encoder_on_the_small_cases():
 
 
 def test_lane_parser_on_the_small_cases():
-    """Batches of up to 4096 waves (<= 8192 samples each) are decoded by parse_wide_kernel (one CTA
+    """Batches of up to 896 waves (<= 8192 samples each) are decoded by parse_wide_kernel (one CTA
     per wave, parallel inside the wave), larger ones by parse_kernel (one lane per wave).
     DRICE_PARSE_WIDE=0 (read once per process) sends EVERY batch to the lane kernel: the edge-case
     suite must stay exact there too."""
