@@ -861,7 +861,7 @@ constexpr uint32_t kWideMaxWaves = 896;                  // measured crossover w
 constexpr int kWideLutBits  = 12;
 
 struct WideCode { uint32_t len; int delta; bool valid; };
-// the code at bit `pos` of the record in shared memory (words padded with two zero words)
+// the code at bit `pos` of the record in shared memory (words padded with four zero words)
 __device__ __forceinline__ WideCode wide_decode_at(const uint32_t *words, const uint32_t *lut, uint32_t pos, int k, uint32_t kmask)
 {
     const uint32_t w = pos >> 5;
@@ -897,8 +897,8 @@ template <bool IDENT>
 __global__ void __launch_bounds__(kWideThreads, 2) parse_wide_kernel(const ParseParams p)
 {
     extern __shared__ __align__(16) uint32_t wsm[];
-    uint32_t *words = wsm;                                       // kWideMaxWords + 2
-    uint32_t *lut = words + kWideMaxWords + 2;                   // 4096
+    uint32_t *words = wsm;                                       // kWideMaxWords + 4 (zero padded: the last run may look past the record)
+    uint32_t *lut = words + kWideMaxWords + 4;                   // 4096
     uint32_t *cnt = lut + (1 << kWideLutBits);                   // per thread: codes / delta sum of its runs
     uint32_t *dsum = cnt + kWideThreads;
     uint8_t *T = reinterpret_cast<uint8_t *>(dsum + kWideThreads);   // [kWideMaxRuns][32] transition functions
@@ -920,7 +920,7 @@ __global__ void __launch_bounds__(kWideThreads, 2) parse_wide_kernel(const Parse
             if (threadIdx.x == 0) atomicOr(p.status, kErrStream);
             continue;
         }
-        for (uint32_t i = threadIdx.x; i < nw + 2; i += kWideThreads) words[i] = i < nw ? p.comp[rec + 1 + i] : 0u;
+        for (uint32_t i = threadIdx.x; i < nw + 4; i += kWideThreads) words[i] = i < nw ? p.comp[rec + 1 + i] : 0u;
         __syncthreads();
         const uint32_t nruns = (nw + kWideRunWords - 1) / kWideRunWords;
         // ---- transition function of every run: lane o enters at bit offset o ---------------------
@@ -1035,7 +1035,7 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
         }
         if ((long)p.nwaves <= wide && p.max_n <= 8192u) {
             static bool wattr = false;
-            const size_t wsmem = (size_t)(kWideMaxWords + 2 + (1 << kWideLutBits) + 2 * kWideThreads) * 4 +
+            const size_t wsmem = (size_t)(kWideMaxWords + 4 + (1 << kWideLutBits) + 2 * kWideThreads) * 4 +
                                  (size_t)kWideMaxRuns * 32 + kWideMaxRuns + 16;
             if (!wattr) {
                 cudaFuncSetAttribute(parse_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);

@@ -78,12 +78,15 @@ void *malloc_prefaulted(size_t bytes)
     if (e > a) madvise((void *)a, e - a, MADV_HUGEPAGE);
     const unsigned nt = 4;
     std::vector<std::thread> th;
-    for (unsigned t = 0; t < nt; ++t)
-        th.emplace_back([=] {
-            volatile char *q = (volatile char *)p;
-            const size_t lo = bytes / nt * t, hi = (t + 1 == nt) ? bytes : bytes / nt * (t + 1);
-            for (size_t i = lo; i < hi; i += 4096) q[i] = 0;
-        });
+    try {                                                // (no exception may cross the C boundary)
+        for (unsigned t = 0; t < nt; ++t)
+            th.emplace_back([=] {
+                volatile char *q = (volatile char *)p;
+                const size_t lo = bytes / nt * t, hi = (t + 1 == nt) ? bytes : bytes / nt * (t + 1);
+                for (size_t i = lo; i < hi; i += 4096) q[i] = 0;
+            });
+    } catch (...) {
+    }
     for (auto &t : th) t.join();
     return p;
 }
@@ -97,12 +100,22 @@ void copy_out(void *dst, const void *src, size_t bytes)
     }
     const unsigned nt = 4;
     std::vector<std::thread> th;
-    for (unsigned t = 0; t < nt; ++t)
-        th.emplace_back([=] {
-            const size_t lo = bytes / nt * t, hi = (t + 1 == nt) ? bytes : bytes / nt * (t + 1);
-            memcpy((char *)dst + lo, (const char *)src + lo, hi - lo);
-        });
+    unsigned started = 0;
+    try {                                                // (no exception may cross the C boundary)
+        for (unsigned t = 0; t < nt; ++t) {
+            th.emplace_back([=] {
+                const size_t lo = bytes / nt * t, hi = (t + 1 == nt) ? bytes : bytes / nt * (t + 1);
+                memcpy((char *)dst + lo, (const char *)src + lo, hi - lo);
+            });
+            ++started;
+        }
+    } catch (...) {
+    }
     for (auto &t : th) t.join();
+    if (started < nt) {                                  // the parts no thread took
+        const size_t lo = bytes / nt * started;
+        memcpy((char *)dst + lo, (const char *)src + lo, bytes - lo);
+    }
 }
 
 void  *g_stage = nullptr;        // pinned landing zone of the encoder's output (guarded by g_mu)
