@@ -8,7 +8,9 @@
  * against (1) the three known-answer streams recorded in SURVEY.md §8c, (2) the prose
  * example of reference docs/Algorithm.md:9, (3) golden vectors produced by the
  * UNMODIFIED reference src/deltaRice.c compiled into oracle/_ref/ (tests/golden/,
- * generator tests/golden/make_golden.py), and (4) oracle/_ref itself when present.
+ * generators tests/golden/make_golden.py and make_golden_filters.py: the latter pins the
+ * generic pre-filter branches, streams and decoded outputs), and (4) oracle/_ref itself
+ * when present.
  *
  * Every function cites the reference lines (relative to /root/reference/) it follows.
  * The code is written from the format description, not transcribed.
