@@ -267,6 +267,10 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries ONE JSON line: NCCL_DEBUG=VERSION (this image's default) makes NCCL print its
+    # version banner there
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — deltarice_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
