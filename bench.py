@@ -267,10 +267,11 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    # stdout carries ONE JSON line: NCCL_DEBUG=VERSION (this image's default) makes NCCL print its
-    # version banner there
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries ONE JSON line: everything else that libraries print to fd 1 (NCCL's version
+    # banner, ...) goes to stderr; the line itself is written to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — deltarice_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
@@ -471,7 +472,8 @@ def run_ours(args):
                                    "api": "one handle: encode the batch, then decode its streams"}},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
     codec.close()
     if world > 1:
         dist.destroy_process_group()
