@@ -853,7 +853,7 @@ __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const Par
 // known entry: counts and delta sums first, a block scan for the sample indices and the inverse
 // delta's running values, then the samples.  32x redundant table lookups, but spread over 512
 // threads and a few SMs that would otherwise idle.
-constexpr int kWideThreads  = 512;
+constexpr int kWideThreads  = 1024;                      // most threads a CTA uses (sizes the per-thread scratch)
 constexpr int kWideRunWords = 4;                         // 128 bits per run
 constexpr int kWideMaxWords = 6400;                      // ceil(25 * 8192 / 32): waves up to 8192 samples
 constexpr int kWideMaxRuns  = kWideMaxWords / kWideRunWords;
@@ -893,21 +893,22 @@ __device__ __forceinline__ WideCode wide_decode_at(const uint32_t *words, const 
     return c;
 }
 
-template <bool IDENT>
-__global__ void __launch_bounds__(kWideThreads, 2) parse_wide_kernel(const ParseParams p)
+// NT threads per CTA: 1024 when there are fewer waves than SMs (more warps per wave), else 512 (two CTAs per SM)
+template <bool IDENT, int NT>
+__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2) parse_wide_kernel(const ParseParams p)
 {
     extern __shared__ __align__(16) uint32_t wsm[];
     uint32_t *words = wsm;                                       // kWideMaxWords + 4 (zero padded: the last run may look past the record)
     uint32_t *lut = words + kWideMaxWords + 4;                   // 4096
     uint32_t *cnt = lut + (1 << kWideLutBits);                   // per thread: codes / delta sum of its runs
-    uint32_t *dsum = cnt + kWideThreads;
-    uint8_t *T = reinterpret_cast<uint8_t *>(dsum + kWideThreads);   // [kWideMaxRuns][32] transition functions
+    uint32_t *dsum = cnt + NT;
+    uint8_t *T = reinterpret_cast<uint8_t *>(dsum + NT);   // [kWideMaxRuns][32] transition functions
     uint8_t *E = T + kWideMaxRuns * 32;                          // [kWideMaxRuns + 1] entry offsets
-    __shared__ uint32_t s_warp_c[kWideThreads / 32], s_warp_d[kWideThreads / 32];
+    __shared__ uint32_t s_warp_c[NT / 32], s_warp_d[NT / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = p.k;
     const uint32_t kmask = (1u << k) - 1u;
-    for (uint32_t i = threadIdx.x; i < (1u << kWideLutBits); i += kWideThreads) lut[i] = make_lut_entry(i, k, kWideLutBits);
+    for (uint32_t i = threadIdx.x; i < (1u << kWideLutBits); i += NT) lut[i] = make_lut_entry(i, k, kWideLutBits);
 
     for (uint32_t g = blockIdx.x; g < p.nwaves; g += gridDim.x) {
         __syncthreads();                                         // (previous wave done with shared memory; LUT built)
@@ -920,11 +921,11 @@ __global__ void __launch_bounds__(kWideThreads, 2) parse_wide_kernel(const Parse
             if (threadIdx.x == 0) atomicOr(p.status, kErrStream);
             continue;
         }
-        for (uint32_t i = threadIdx.x; i < nw + 4; i += kWideThreads) words[i] = i < nw ? p.comp[rec + 1 + i] : 0u;
+        for (uint32_t i = threadIdx.x; i < nw + 4; i += NT) words[i] = i < nw ? p.comp[rec + 1 + i] : 0u;
         __syncthreads();
         const uint32_t nruns = (nw + kWideRunWords - 1) / kWideRunWords;
         // ---- transition function of every run: lane o enters at bit offset o ---------------------
-        for (uint32_t r = warp; r < nruns; r += kWideThreads / 32) {
+        for (uint32_t r = warp; r < nruns; r += NT / 32) {
             const uint32_t end = (r + 1) * (kWideRunWords * 32);
             uint32_t pos = r * (kWideRunWords * 32) + (uint32_t)lane;
             while (pos < end) pos += wide_decode_at(words, lut, pos, k, kmask).len;
@@ -941,7 +942,7 @@ __global__ void __launch_bounds__(kWideThreads, 2) parse_wide_kernel(const Parse
         }
         __syncthreads();
         // ---- every thread takes consecutive runs: codes and delta sum first ---------------------
-        const uint32_t rpt = (nruns + kWideThreads - 1) / kWideThreads;
+        const uint32_t rpt = (nruns + NT - 1) / NT;
         const uint32_t r0 = threadIdx.x * rpt, r1 = min(r0 + rpt, nruns);
         uint32_t c = 0, dsm = 0;
         for (uint32_t r = r0; r < r1; ++r) {
@@ -965,7 +966,7 @@ __global__ void __launch_bounds__(kWideThreads, 2) parse_wide_kernel(const Parse
         __syncthreads();
         uint32_t bc = 0, bd = 0, total = 0;
 #pragma unroll
-        for (int w = 0; w < kWideThreads / 32; ++w) {
+        for (int w = 0; w < NT / 32; ++w) {
             if (w < warp) { bc += s_warp_c[w]; bd += s_warp_d[w]; }
             total += s_warp_c[w];
         }
@@ -1038,13 +1039,20 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
             const size_t wsmem = (size_t)(kWideMaxWords + 4 + (1 << kWideLutBits) + 2 * kWideThreads) * 4 +
                                  (size_t)kWideMaxRuns * 32 + kWideMaxRuns + 16;
             if (!wattr) {
-                cudaFuncSetAttribute(parse_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
-                cudaFuncSetAttribute(parse_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+                cudaFuncSetAttribute(parse_wide_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+                cudaFuncSetAttribute(parse_wide_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+                cudaFuncSetAttribute(parse_wide_kernel<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+                cudaFuncSetAttribute(parse_wide_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
                 wattr = true;
             }
-            const uint32_t wgrid = p.nwaves < (uint32_t)(2 * g_dec_sms) ? p.nwaves : (uint32_t)(2 * g_dec_sms);
-            if (p.identity) parse_wide_kernel<true><<<wgrid, kWideThreads, wsmem, st>>>(p);
-            else            parse_wide_kernel<false><<<wgrid, kWideThreads, wsmem, st>>>(p);
+            if (p.nwaves <= (uint32_t)g_dec_sms) {           // fewer waves than SMs: the biggest CTA per wave
+                if (p.identity) parse_wide_kernel<true, 1024><<<p.nwaves, 1024, wsmem, st>>>(p);
+                else            parse_wide_kernel<false, 1024><<<p.nwaves, 1024, wsmem, st>>>(p);
+            } else {
+                const uint32_t wgrid = p.nwaves < (uint32_t)(2 * g_dec_sms) ? p.nwaves : (uint32_t)(2 * g_dec_sms);
+                if (p.identity) parse_wide_kernel<true, 512><<<wgrid, 512, wsmem, st>>>(p);
+                else            parse_wide_kernel<false, 512><<<wgrid, 512, wsmem, st>>>(p);
+            }
             return 1;
         }
     }
