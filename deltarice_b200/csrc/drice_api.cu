@@ -175,9 +175,21 @@ int small_copy(drice_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStr
     return DRICE_OK;
 }
 
-// uploads [chunk_sample_off u64 (n+1)] [second u64 table (n+1), optional] [wave_off u32 (n+1)]
+// one launch prepares a call: the tables come over from mapped host memory, the scratch range the
+// kernels expect zeroed (tickets, look-back words) is cleared, the status word reset
+__global__ void prep_kernel(uint32_t *dst, const uint32_t *src, uint32_t nwords, uint4 *zero, size_t zero_vec, uint32_t *status)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < nwords; i += nth) dst[i] = src[i];
+    for (size_t i = tid; i < zero_vec; i += nth) zero[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0 && status) *status = 0;
+}
+
+// uploads [chunk_sample_off u64 (n+1)] [second u64 table (n+1), optional] [wave_off u32 (n+1)], zeroes
+// `zero_bytes` (rounded up to 16) at `zero_p` (16-byte aligned, may be null) and resets *status
 int upload_tables(drice_ctx *ctx, const uint64_t *t0, const uint64_t *t1, const uint32_t *wave_off,
-                  size_t nchunks, cudaStream_t st, uint64_t **d_t0, uint64_t **d_t1, uint32_t **d_w)
+                  size_t nchunks, cudaStream_t st, uint64_t **d_t0, uint64_t **d_t1, uint32_t **d_w,
+                  void *zero_p, size_t zero_bytes, uint32_t *status)
 {
     const size_t n1 = nchunks + 1;
     const size_t bytes = n1 * 8 * 2 + n1 * 4;
@@ -200,7 +212,15 @@ int upload_tables(drice_ctx *ctx, const uint64_t *t0, const uint64_t *t1, const 
     memcpy(h, t0, n1 * 8);
     if (t1) memcpy(h + n1 * 8, t1, n1 * 8); else memset(h + n1 * 8, 0, n1 * 8);
     memcpy(h + n1 * 16, wave_off, n1 * 4);
-    { int rc_ = small_copy(ctx, ctx->d_tab.p, h, bytes, st); if (rc_) return rc_; }
+    {
+        const size_t zero_vec = zero_p ? (zero_bytes + 15) / 16 : 0;
+        size_t work = std::max<size_t>(bytes / 4, zero_vec);
+        unsigned grid = (unsigned)std::min<size_t>((work + 255) / 256, 296);
+        if (grid < 1) grid = 1;
+        prep_kernel<<<grid, 256, 0, st>>>((uint32_t *)ctx->d_tab.p, (const uint32_t *)h, (uint32_t)(bytes / 4), (uint4 *)zero_p, zero_vec, status);
+        DR_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
     DR_CUDA(ctx, cudaEventRecord(ctx->ev_tab, st));
     ctx->ev_tab_pending = true;
     *d_t0 = (uint64_t *)ctx->d_tab.p;
@@ -478,25 +498,25 @@ extern "C" int drice_encode_batch_dev_async(drice_ctx *ctx, const int16_t *d_raw
     Geometry g;
     int rc = build_geometry(ctx, off, nchunks, L, true, g);
     if (rc) return rc;
-    DR_CUDA(ctx, cudaMemsetAsync(d_status, 0, sizeof(uint32_t), st));
     if (nchunks == 0) {
+        DR_CUDA(ctx, cudaMemsetAsync(d_status, 0, sizeof(uint32_t), st));
         DR_CUDA(ctx, cudaMemsetAsync(d_chunk_byte_off, 0, sizeof(uint64_t), st));
         return DRICE_OK;
     }
     if (!d_raw && off[nchunks] > 0) return fail(ctx, DRICE_E_PARAM, "null input");
-    uint64_t *d_soff, *d_unused;
-    uint32_t *d_woff;
-    rc = upload_tables(ctx, off, nullptr, g.wave_off.data(), nchunks, st, &d_soff, &d_unused, &d_woff);
-    if (rc) return rc;
     // scratch: [ticket u32][pad] | look-back status u64 per tile (at most one per wave) | slices done
     // u32 per lane-kernel task: all zeroed; then the parked lane states (not zeroed)
     const size_t ntasks = ((size_t)g.nwaves + 31) / 32;
-    const size_t zeroed = (size_t)g.nwaves * 8 + 16 + ntasks * 4 + 16;
+    const size_t zeroed = ((size_t)g.nwaves * 8 + 16 + ntasks * 4 + 16 + 15) & ~(size_t)15;
     const size_t state_off = (zeroed + 255) & ~(size_t)255;
     const size_t scratch = state_off + ntasks * 6 * 32 * 4;
     if (scratch > ctx->d_scratch.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
     DR_CUDA(ctx, ctx->d_scratch.reserve(scratch));
-    DR_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch.p, 0, zeroed, st));
+    uint64_t *d_soff, *d_unused;
+    uint32_t *d_woff;
+    rc = upload_tables(ctx, off, nullptr, g.wave_off.data(), nchunks, st, &d_soff, &d_unused, &d_woff,
+                       ctx->d_scratch.p, zeroed, d_status);
+    if (rc) return rc;
 
     const int16_t *src = d_raw;
     if (ctx->filter_mode == 2) {
@@ -618,8 +638,10 @@ extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_co
     Geometry g;
     int rc = build_geometry(ctx, off, nchunks, L, false, g);
     if (rc) return rc;
-    DR_CUDA(ctx, cudaMemsetAsync(d_status, 0, sizeof(uint32_t), st));
-    if (nchunks == 0) return DRICE_OK;
+    if (nchunks == 0) {
+        DR_CUDA(ctx, cudaMemsetAsync(d_status, 0, sizeof(uint32_t), st));
+        return DRICE_OK;
+    }
     std::vector<uint64_t> woff(nchunks + 1);
     for (size_t c = 0; c <= nchunks; ++c) {
         if ((boff[c] & 3) || (c && boff[c] < boff[c - 1] + 4))
@@ -627,15 +649,15 @@ extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_co
         woff[c] = boff[c] / 4;
     }
     if (!d_comp) return fail(ctx, DRICE_E_PARAM, "null input");
-    uint64_t *d_soff, *d_woff64;
-    uint32_t *d_wave_off;
-    rc = upload_tables(ctx, off, woff.data(), g.wave_off.data(), nchunks, st, &d_soff, &d_woff64, &d_wave_off);
-    if (rc) return rc;
     const size_t nw = g.nwaves;
     const size_t scratch = nw * (8 + 8 + 4) + 64 + 16;
     if (scratch > ctx->d_scratch.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
     DR_CUDA(ctx, ctx->d_scratch.reserve(scratch));
-    DR_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch.p, 0, 16, st));      // parse ticket
+    uint64_t *d_soff, *d_woff64;
+    uint32_t *d_wave_off;
+    rc = upload_tables(ctx, off, woff.data(), g.wave_off.data(), nchunks, st, &d_soff, &d_woff64, &d_wave_off,
+                       ctx->d_scratch.p, 16, d_status);      // (16 bytes: the parse ticket)
+    if (rc) return rc;
     uint64_t *wave_in = (uint64_t *)((char *)ctx->d_scratch.p + 16);
     uint64_t *wave_out = wave_in + nw;
     uint32_t *wave_n = (uint32_t *)(wave_out + nw);
