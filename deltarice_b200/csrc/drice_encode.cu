@@ -483,7 +483,7 @@ __device__ __forceinline__ uint32_t encode_wave(const int16_t *wave, uint32_t n,
 }
 
 // ---- tile kernel ----------------------------------------------------------------------------
-// A tile = kEncWarps consecutive waves, taken by one persistent CTA of kEncWarps worker warps +
+// A tile = NW consecutive waves, taken by one persistent CTA of NW worker warps +
 // one control warp.  Per iteration a worker encodes ONE wave of the current tile into one of its
 // two staging buffers (single sweep over HBM), then copies out the wave it encoded in the
 // previous iteration, whose position has been resolved in the meantime:
@@ -496,19 +496,22 @@ __device__ __forceinline__ uint32_t encode_wave(const int16_t *wave, uint32_t n,
 // done with it.
 constexpr int kRing = 3;
 
-template <int K, int MINB, bool kDelta>
-__global__ void __launch_bounds__((kEncWarps + 1) * 32, MINB)
+// NW worker warps (+ 1 control warp) per CTA: 12 for short waves (two CTAs per SM: measured best,
+// 0.69 vs 0.74 ms for 3 x 8 on C2; 13 and 14 lose to register pressure), 8 when the staging of
+// longer waves needs the room
+template <int K, int MINB, bool kDelta, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, MINB)
 encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint32_t ntiles)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t s_tile[kRing];                   // tile index of the iteration
-    __shared__ uint32_t s_mine[kRing][kEncWarps];        // words each wave contributes
+    __shared__ uint32_t s_mine[kRing][NW];        // words each wave contributes
     __shared__ uint32_t s_cnt[kRing];                    // workers that have reported
     __shared__ uint32_t s_total[kRing];
     __shared__ uint64_t s_off[kRing];                    // tile's exclusive word offset
     __shared__ volatile uint32_t s_flag[kRing];          // = it + 1 once s_off is valid
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool control = warp == kEncWarps;
+    const bool control = warp == NW;
 
     if (threadIdx.x < kRing) { s_flag[threadIdx.x] = 0; s_cnt[threadIdx.x] = 0; }
     if (threadIdx.x == 0) s_tile[0] = atomicAdd(p.ticket, 1u);
@@ -551,7 +554,7 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
         uint32_t nwords = 0;
         bool have = false, ovf = false;
         if (live) {
-            const uint32_t g = tile * kEncWarps + warp;
+            const uint32_t g = tile * NW + warp;
             uint32_t mine = 0;
             if (g < p.nwaves) {
                 have = true;
@@ -570,12 +573,12 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
             if (lane == 0) {
                 s_mine[slot][warp] = mine;
                 __threadfence_block();
-                if (atomicAdd(&s_cnt[slot], 1u) == kEncWarps - 1) {
+                if (atomicAdd(&s_cnt[slot], 1u) == NW - 1) {
                     // last worker of the tile: publish the tile's aggregate now
                     __threadfence_block();
                     uint32_t total = 0;
 #pragma unroll
-                    for (int w = 0; w < kEncWarps; ++w) total += s_mine[slot][w];
+                    for (int w = 0; w < NW; ++w) total += s_mine[slot][w];
                     st_relaxed_u64(p.lookback + tile, kFlagAggregate | (uint64_t)total);
                     s_total[slot] = total;
                     s_cnt[slot] = 0;
@@ -594,7 +597,7 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
             const int ps = (it + kRing - 1) % kRing;
             while (s_flag[ps] != it) __nanosleep(40);        // tile offset: normally there long ago
             __threadfence_block();
-            const uint32_t v = lane < kEncWarps ? s_mine[ps][lane] : 0u;
+            const uint32_t v = lane < NW ? s_mine[ps][lane] : 0u;
             const uint32_t loff = __reduce_add_sync(0xffffffffu, lane < warp ? v : 0u);
             const uint64_t off = s_off[ps] + loff;
             const uint32_t rec_words = wg_prev.chunk_total ? nwords_prev + 1u : 0u;
@@ -625,7 +628,7 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
         have_prev = have;
         ovf_prev = ovf;
         // workers only (the control warp runs on its own clock)
-        asm volatile("bar.sync 1, %0;" ::"n"(kEncWarps * 32) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
     }
 }
 
@@ -1258,21 +1261,21 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
     }
     // per-warp staging (two buffers per worker warp): room for ~10 bits per sample, at most the
     // worst case; a wave that outgrows it is packed straight into its record in HBM.  Short
-    // waves leave room for three CTAs per SM (72 registers), longer ones run two (more registers).
+    // waves: 12 worker warps per CTA, two CTAs per SM; longer ones: 8 worker warps (larger staging).
     const uint32_t worst = (25u * max_wave_len + 31u) / 32u + 24u;
     uint32_t stage = (10u * max_wave_len + 31u) / 32u + 24u;
     const char *e = getenv("DRICE_ENC_STAGE_WORDS");
-    const bool three = !e && stage <= 1120u;
+    const bool twelve = !e && md.delta && stage <= 1120u;
     if (e) stage = (uint32_t)atol(e);
-    else if (three) stage = stage < 1088u ? stage : 1088u;
+    else if (stage <= 1120u) stage = stage < 1088u ? stage : 1088u;
     else stage = 1600u;
     if (stage > worst) stage = worst;
     if (stage < 64u) stage = 64u;
     stage = (stage + 3u) & ~3u;
-    const size_t smem = (size_t)stage * 2 * kEncWarps * sizeof(uint32_t);   // two buffers per worker warp
-    const int nthreads = (kEncWarps + 1) * 32;
-    const uint32_t ntiles = (p.nwaves + kEncWarps - 1) / kEncWarps;
-    auto launch = [&](auto kernel, bool &attr_set) {
+    auto launch = [&](auto kernel, bool &attr_set, int nworkers) {
+        const size_t smem = (size_t)stage * 2 * nworkers * sizeof(uint32_t);   // two buffers per worker warp
+        const int nthreads = (nworkers + 1) * 32;
+        const uint32_t ntiles = (p.nwaves + nworkers - 1) / nworkers;
         if (!attr_set) {
             cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -1285,10 +1288,10 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
         if (grid > ntiles) grid = ntiles;
         kernel<<<grid, nthreads, smem, st>>>(p, stage, ntiles);
     };
-    static bool attr3 = false, attr2 = false, attr2n = false;   // per K (this function is a template)
-    if (!md.delta) launch(encode_tile_kernel<K, 2, false>, attr2n);    // no delta (filter [1] / pre-filtered input)
-    else if (three) launch(encode_tile_kernel<K, 3, true>, attr3);
-    else launch(encode_tile_kernel<K, 2, true>, attr2);
+    static bool attr12 = false, attr8 = false, attr8n = false;   // per K (this function is a template)
+    if (!md.delta) launch(encode_tile_kernel<K, 2, false, 8>, attr8n, 8);    // no delta (filter [1] / pre-filtered input)
+    else if (twelve) launch(encode_tile_kernel<K, 2, true, 12>, attr12, 12);
+    else launch(encode_tile_kernel<K, 2, true, 8>, attr8, 8);
     return 1;
 }
 

@@ -17,7 +17,6 @@ constexpr int      kSamplesPerThread = 16;   // one 32-byte aligned slot per thr
 constexpr uint32_t kEscapeQuotient   = 8;    // reference "giveup", src/deltaRice.c:203
 constexpr uint32_t kEscapeBits       = 25;   // 8 zeros + 1 + 16 value bits
 constexpr int      kEncMaxThreads    = 512;  // CTA size of the long-wave / redo kernels
-constexpr int      kEncWarps         = 8;    // worker warps per CTA of the tile kernel (+1 control warp)
 constexpr int      kEncWavesPerWarp  = 1;    // waves per worker warp and tile
 constexpr int      kEncTileMaxL      = 8192; // longest wave the warp-per-wave kernel takes
 
