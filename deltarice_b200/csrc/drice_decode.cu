@@ -6,20 +6,21 @@
 //   decompressWithRiceCoding        src/deltaRice.c:138-189
 //   decodeWaveform delta branch     src/deltaRice.c:78-90
 //
-// Two kernels:
-//   locate_kernel  one CTA per chunk.  The stream has no index, only the chain
-//                  cur += word[cur] + 1 (:319-325); chasing it through HBM would cost one
-//                  DRAM round trip per wave, so one thread streams the chunk through shared
-//                  memory (bulk async copies on mbarriers, 128 KB in flight) and chases the
-//                  chain at shared-memory latency, writing the record positions; the other
-//                  warps fill the rest of the per-wave table (output position, sample count).
-//   parse_kernel   one THREAD per wave, 32 waves per warp: Rice parsing is a serial chain
-//                  per wave, so the parallelism is across waves.  Each lane streams its
-//                  record through a private shared-memory ring (128-bit loads issued one
-//                  group ahead), finds the unary terminator with one count-leading-zeros on
-//                  a funnel-shifted 32-bit window, rebuilds the sample with a running sum
-//                  (inverse delta, wraps mod 2^16) and writes it to a per-warp shared tile
-//                  that the warp then stores to HBM row by row, coalesced.
+// Locating the records of a chunk (the stream has no index, only the chain cur += word[cur] + 1):
+//   scan_headers_kernel + rank_headers_kernel   waves of a few thousand samples: headers are FOUND
+//                  by their value range on all SMs, ranked per chunk and verified against the chain;
+//                  anything inconsistent falls back to the exact serial chase
+//   locate_kernel  short waves / very long waves: one CTA per chunk streams the chunk through a
+//                  128 KB circular buffer in shared memory (bulk async copies on mbarriers) while ONE
+//                  thread chases the chain at shared-memory latency
+// Decoding the records:
+//   parse_kernel   one LANE per wave, 32 waves per warp: Rice parsing is a serial chain per wave, so
+//                  the parallelism is across waves.  One register of state per lane
+//                  (sample << 16 | bit position), one table lookup and one add per code, several
+//                  codes per 64-bit window, 16 samples per 32-byte store
+//   parse_wide_kernel   batches too small to fill the machine with lanes: one CTA per wave,
+//                  parallel INSIDE the wave (transition functions of four-word runs composed along
+//                  the record, then the runs decode independently)
 #include "drice_kernels.cuh"
 
 #include <cstdio>
