@@ -67,29 +67,52 @@ H5Z_class_t H5Z_DELTARICE[1] = {{
 namespace {
 // The buffer handed back to libhdf5 must come from malloc (libhdf5 frees it).  For a multi-MB chunk
 // glibc maps fresh pages, and faulting them in one by one inside the device-to-host copy costs more
-// than the codec (28 MB: ~10 ms against ~1 ms of GPU work).  Ask for huge pages and touch the pages
-// from a few threads before the copy lands.
-void *malloc_prefaulted(size_t bytes)
-{
-    void *p = malloc(bytes ? bytes : 1);
-    if (!p || bytes < (4u << 20)) return p;
-    const uintptr_t a = ((uintptr_t)p + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1);
-    const uintptr_t e = ((uintptr_t)p + bytes) & ~(uintptr_t)((2u << 20) - 1);
-    if (e > a) madvise((void *)a, e - a, MADV_HUGEPAGE);
-    const unsigned nt = 4;
+// than the codec (28 MB: ~10 ms against ~1 ms of GPU work).  Ask for huge pages and populate the
+// pages from a few threads WHILE the stream goes to the device and the kernels run:
+// MADV_POPULATE_WRITE faults pages in without touching their contents, so it cannot race with the
+// copy that fills the buffer afterwards (kernels older than 5.14: touch the pages up front instead).
+#ifndef MADV_POPULATE_WRITE
+#define MADV_POPULATE_WRITE 23
+#endif
+struct Prefault {
     std::vector<std::thread> th;
-    try {                                                // (no exception may cross the C boundary)
-        for (unsigned t = 0; t < nt; ++t)
-            th.emplace_back([=] {
-                volatile char *q = (volatile char *)p;
-                const size_t lo = bytes / nt * t, hi = (t + 1 == nt) ? bytes : bytes / nt * (t + 1);
-                for (size_t i = lo; i < hi; i += 4096) q[i] = 0;
-            });
-    } catch (...) {
+    void *p = nullptr;
+    void start(size_t bytes)
+    {
+        p = malloc(bytes ? bytes : 1);
+        if (!p || bytes < (4u << 20)) return;
+        const uintptr_t a = ((uintptr_t)p + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1);
+        const uintptr_t e = ((uintptr_t)p + bytes) & ~(uintptr_t)((2u << 20) - 1);
+        if (e > a) madvise((void *)a, e - a, MADV_HUGEPAGE);
+        // probe: is MADV_POPULATE_WRITE there?
+        const uintptr_t pg = ((uintptr_t)p + 4095) & ~(uintptr_t)4095;
+        const bool populate = madvise((void *)pg, 4096, MADV_POPULATE_WRITE) == 0;
+        const unsigned nt = 4;
+        void *base = p;
+        try {                                            // (no exception may cross the C boundary)
+            for (unsigned t = 0; t < nt; ++t)
+                th.emplace_back([=] {
+                    const size_t lo = bytes / nt * t, hi = (t + 1 == nt) ? bytes : bytes / nt * (t + 1);
+                    if (populate) {
+                        const uintptr_t l = ((uintptr_t)base + lo + 4095) & ~(uintptr_t)4095;
+                        const uintptr_t h = ((uintptr_t)base + hi) & ~(uintptr_t)4095;
+                        if (h > l) madvise((void *)l, h - l, MADV_POPULATE_WRITE);
+                    } else {
+                        volatile char *q = (volatile char *)base;
+                        for (size_t i = lo; i < hi; i += 4096) q[i] = 0;
+                    }
+                });
+        } catch (...) {
+        }
+        if (!populate) join();                           // plain touches must be done before the data arrives
     }
-    for (auto &t : th) t.join();
-    return p;
-}
+    void join()
+    {
+        for (auto &t : th) t.join();
+        th.clear();
+    }
+    ~Prefault() { join(); }
+};
 
 // memcpy into freshly malloc'ed memory, page faults spread over a few threads for multi-MB streams
 void copy_out(void *dst, const void *src, size_t bytes)
@@ -154,11 +177,14 @@ size_t H5Z_filter_deltarice(unsigned flags, size_t cd_nelmts, const unsigned cd_
         memcpy(&total, *buf, 4);
         if (total > 0x7fffffffu) return 0;
         const size_t out_bytes = (size_t)total * 2;
-        void *out = malloc_prefaulted(out_bytes);
+        Prefault pf;
+        pf.start(out_bytes);
+        void *out = pf.p;
         if (!out) return 0;
         const uint64_t boff[2] = {0, nbytes};
         const uint64_t soff[2] = {0, total};
         const int rc = drice_decode_batch_host(ctx, *buf, boff, 1, soff, prm.M, prm.L, (int16_t *)out);
+        pf.join();
         if (rc != DRICE_OK) {
             fprintf(stderr, "deltarice_b200: de-compression failed: %s\n", drice_last_error(ctx));
             free(out);
