@@ -5,7 +5,8 @@
 
 A "step" is one pass of the hot path over one batch of synthetic input: ENCODE the batch
 (raw int16 -> Delta-Rice chunk streams), [N>1: all-gather the per-shard byte counts + scan],
-then DECODE the streams back (-> raw int16).  Workload at every N (weak scaling, one
+then DECODE the streams back (-> raw int16); the all-gather runs on a side stream next to the
+decode kernels and is joined before the step ends.  Workload at every N (weak scaling, one
 process per GPU): BASELINE.json configs[1] "C2" per GPU — 153 391 Nab-like waveforms of
 3500 samples (1.074 GB raw), RiceParameter M=4, chunks of 2000 waveforms.
 
@@ -313,12 +314,24 @@ def run_ours(args):
     assert int(d_status[0]) == 0 and torch.equal(x, y), "decode(encode(x)) != x"
     ratio = comp_bytes / raw_bytes
 
+    # the path's one exchange (per-shard byte counts -> offsets in the concatenated stream) needs the
+    # encoder's result but nothing of the decoder: it runs on a side stream next to the decode kernels
+    # and is joined before the step ends
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+
+    def exchange():
+        cur = torch.cuda.current_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            shard.gather_shard_offsets(d_boff[nchunks:nchunks + 1])
+
     def step():
         codec.encode_device_async(x, off, M, L, out, d_boff, d_status)
         if world > 1:
-            # the path's one exchange: per-shard byte counts -> offsets in the concatenated stream
-            shard.gather_shard_offsets(d_boff[nchunks:nchunks + 1])
+            exchange()
         codec.decode_device_async(comp, boff, off, M, L, y, d_status)
+        if world > 1:
+            torch.cuda.current_stream(dev).wait_stream(side)
 
     def barrier():
         if world > 1:
@@ -341,10 +354,12 @@ def run_ours(args):
     ev[0].record()
     for s in range(args.steps):
         codec.encode_device_async(x, off, M, L, out, d_boff, d_status)
-        if world > 1:
-            shard.gather_shard_offsets(d_boff[nchunks:nchunks + 1])
         ev[2 * s + 1].record()
+        if world > 1:
+            exchange()
         codec.decode_device_async(comp, boff, off, M, L, y, d_status)
+        if world > 1:
+            torch.cuda.current_stream(dev).wait_stream(side)
         ev[2 * s + 2].record()
     barrier()
     clocks.live(False)
