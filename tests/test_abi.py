@@ -99,3 +99,12 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f
+
+
+def test_chunk_grid_follows_hdf5_order():
+    """deltarice_b200.h5.chunk_grid: chunk origins in libhdf5's row-major order, edge chunks included."""
+    from deltarice_b200 import h5
+    assert h5.chunk_grid((100, 7000), (20, 7000)) == [(0, 0), (20, 0), (40, 0), (60, 0), (80, 0)]
+    g = h5.chunk_grid((50, 333), (16, 128))
+    assert len(g) == 4 * 3 and g[0] == (0, 0) and g[1] == (0, 128) and g[3] == (16, 0) and g[-1] == (48, 256)
+    assert h5.chunk_grid((7,), (3,)) == [(0,), (3,), (6,)]
