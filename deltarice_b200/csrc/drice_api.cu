@@ -13,8 +13,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace drice;
@@ -65,6 +68,9 @@ struct drice_ctx {
     DevBuf d_filt;                       // generic filter: pre-filtered samples of the batch
     DevBuf d_lane;                       // lane-per-wave encoder: one worst-case slot per wave
     DevBuf d_scan;                       // locate by scanning: per-tile header candidates
+    // pageable caller buffers: two pinned pieces the copies are staged through (see staged_h2d)
+    char *h_piece[2] = {nullptr, nullptr};
+    cudaEvent_t ev_piece[2] = {nullptr, nullptr};
 
     // optional per-kernel timing (drice_timing_*): event pairs recorded around launches
     bool timing = false;
@@ -403,6 +409,10 @@ extern "C" void drice_destroy(drice_ctx *ctx)
     for (auto &t : ctx->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     ctx->d_tab.release(); ctx->d_scratch.release(); ctx->d_offs.release(); ctx->d_filt.release(); ctx->d_lane.release(); ctx->d_scan.release();
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->h_piece[i]) cudaFreeHost(ctx->h_piece[i]);
+        if (ctx->ev_piece[i]) cudaEventDestroy(ctx->ev_piece[i]);
+    }
     if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
     if (ctx->h_sync) cudaFreeHost(ctx->h_sync);
     if (ctx->ev_tab) cudaEventDestroy(ctx->ev_tab);
@@ -749,6 +759,168 @@ extern "C" int drice_decode_batch_dev(drice_ctx *ctx, const uint32_t *d_comp, co
 // ======================================================================================
 namespace {
 
+// ---- pageable caller buffers ---------------------------------------------------------
+// libhdf5 hands the filter malloc'ed (pageable) memory.  cudaMemcpyAsync on pageable memory is a
+// synchronous staged copy at ~12 GB/s; PCIe 5 x16 moves 55.  Large pageable transfers are therefore
+// staged HERE: 4 MB pieces through two pinned buffers, the memcpy of a piece split over a small
+// pool of host threads, piece i+1 being copied while piece i is on the bus.
+constexpr size_t kPieceBytes = 4u << 20;
+constexpr size_t kStagedMin = 8u << 20;      // smaller transfers: leave it to the driver
+
+class CopyPool {
+public:
+    static CopyPool &get()
+    {
+        static CopyPool pool;
+        return pool;
+    }
+    // memcpy split in kParts; returns when all of it is done
+    void copy(char *dst, const char *src, size_t n)
+    {
+        if (!ok_ || n < (1u << 20)) {
+            memcpy(dst, src, n);
+            return;
+        }
+        const size_t part = (n / kParts + 63) & ~(size_t)63;
+        int mine = 0;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            for (int i = 1; i < kParts; ++i) {
+                const size_t lo = part * i;
+                if (lo >= n) break;
+                q_.push_back({dst + lo, src + lo, std::min(part, n - lo)});
+                ++mine;
+            }
+            pending_ += mine;
+        }
+        cv_.notify_all();
+        memcpy(dst, src, std::min(part, n));
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+    }
+
+private:
+    static constexpr int kParts = 4;
+    struct Job { char *dst; const char *src; size_t n; };
+    CopyPool()
+    {
+        try {
+            for (int i = 0; i < kParts - 1; ++i) th_.emplace_back([this] { run(); });
+            ok_ = true;
+        } catch (...) {
+            ok_ = false;
+        }
+    }
+    ~CopyPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    void run()
+    {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                j = q_.front();
+                q_.pop_front();
+            }
+            memcpy(j.dst, j.src, j.n);
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                --pending_;
+            }
+            done_.notify_all();
+        }
+    }
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    std::deque<Job> q_;
+    std::vector<std::thread> th_;
+    int pending_ = 0;
+    bool stop_ = false, ok_ = false;
+};
+
+bool is_pageable(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+int ensure_pieces(drice_ctx *ctx)
+{
+    for (int i = 0; i < 2; ++i) {
+        if (!ctx->h_piece[i]) DR_CUDA(ctx, cudaMallocHost((void **)&ctx->h_piece[i], kPieceBytes));
+        if (!ctx->ev_piece[i]) DR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_piece[i], cudaEventDisableTiming));
+    }
+    return DRICE_OK;
+}
+
+// host -> device on `st`; the source may be reused when the call returns iff it was staged
+// (pageable); pinned sources follow the usual asynchronous rules
+int h2d(drice_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, cudaStream_t st)
+{
+    if (bytes < kStagedMin || !is_pageable(h_src)) {
+        DR_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+        return DRICE_OK;
+    }
+    int rc = ensure_pieces(ctx);
+    if (rc) return rc;
+    size_t off = 0;
+    for (int i = 0; off < bytes; ++i) {
+        const int sl = i & 1;
+        const size_t n = std::min(kPieceBytes, bytes - off);
+        if (i >= 2) DR_CUDA(ctx, cudaEventSynchronize(ctx->ev_piece[sl]));
+        CopyPool::get().copy(ctx->h_piece[sl], (const char *)h_src + off, n);
+        DR_CUDA(ctx, cudaMemcpyAsync((char *)d_dst + off, ctx->h_piece[sl], n, cudaMemcpyHostToDevice, st));
+        DR_CUDA(ctx, cudaEventRecord(ctx->ev_piece[sl], st));
+        off += n;
+    }
+    // the pieces are reused by the next staged transfer: drain
+    DR_CUDA(ctx, cudaEventSynchronize(ctx->ev_piece[0]));
+    DR_CUDA(ctx, cudaEventSynchronize(ctx->ev_piece[1]));
+    return DRICE_OK;
+}
+
+// device -> host on `st`.  Returns true in *done when the data is already in h_dst (staged path:
+// the call waited for it); otherwise the copy is in flight on `st` as usual
+int d2h(drice_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, cudaStream_t st, bool *done)
+{
+    *done = false;
+    if (bytes < kStagedMin || !is_pageable(h_dst)) {
+        DR_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+        return DRICE_OK;
+    }
+    int rc = ensure_pieces(ctx);
+    if (rc) return rc;
+    const size_t npieces = (bytes + kPieceBytes - 1) / kPieceBytes;
+    auto issue = [&](size_t i) -> cudaError_t {
+        const size_t off = i * kPieceBytes, n = std::min(kPieceBytes, bytes - off);
+        cudaError_t e = cudaMemcpyAsync(ctx->h_piece[i & 1], (const char *)d_src + off, n, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return e;
+        return cudaEventRecord(ctx->ev_piece[i & 1], st);
+    };
+    DR_CUDA(ctx, issue(0));
+    for (size_t i = 0; i < npieces; ++i) {
+        DR_CUDA(ctx, cudaEventSynchronize(ctx->ev_piece[i & 1]));
+        if (i + 1 < npieces) DR_CUDA(ctx, issue(i + 1));          // the other piece is free: its copy-out was i-1
+        const size_t off = i * kPieceBytes, n = std::min(kPieceBytes, bytes - off);
+        CopyPool::get().copy((char *)h_dst + off, ctx->h_piece[i & 1], n);
+    }
+    *done = true;
+    return DRICE_OK;
+}
+
 size_t subbatch_bytes()
 {
     static size_t v = 0;
@@ -819,7 +991,8 @@ extern "C" int drice_encode_batch_host(drice_ctx *ctx, const int16_t *h_raw, con
         const uint64_t bytes = s.h_offs_pinned[n];
         if (out_pos + bytes > out_cap_bytes) return fail(ctx, DRICE_E_CAPACITY, "output buffer too small for the compressed batch");
         for (size_t c = 0; c <= n; ++c) chunk_byte_off[s.c0 + c] = out_pos + s.h_offs_pinned[c];
-        DR_CUDA(ctx, cudaMemcpyAsync((char *)h_out + out_pos, s.comp.p, bytes, cudaMemcpyDeviceToHost, ctx->s_out));
+        bool landed = false;
+        { int r2 = d2h(ctx, (char *)h_out + out_pos, s.comp.p, bytes, ctx->s_out, &landed); if (r2) return r2; }
         DR_CUDA(ctx, cudaEventRecord(s.ev_out, ctx->s_out));
         out_pos += bytes;
         return DRICE_OK;
@@ -843,7 +1016,7 @@ extern "C" int drice_encode_batch_host(drice_ctx *ctx, const int16_t *h_raw, con
             DR_CUDA(ctx, s.raw.reserve((s1 - s0) * 2 + 64));
             DR_CUDA(ctx, s.comp.reserve(bound));
             if ((rc = slot_offs_reserve(ctx, s, n))) break;
-            DR_CUDA(ctx, cudaMemcpyAsync(s.raw.p, h_raw + s0, (s1 - s0) * 2, cudaMemcpyHostToDevice, ctx->s_in));
+            if ((rc = h2d(ctx, s.raw.p, h_raw + s0, (s1 - s0) * 2, ctx->s_in))) break;
             DR_CUDA(ctx, cudaEventRecord(s.ev_in, ctx->s_in));
             DR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_in, 0));
             uint64_t *d_offs = (uint64_t *)s.offs.p;
@@ -894,7 +1067,8 @@ extern "C" int drice_decode_batch_host(drice_ctx *ctx, const void *h_comp, const
         int r = status_to_error(ctx, *(uint32_t *)s.h_offs_pinned);
         if (r) return r;
         const uint64_t s0 = off[s.c0], s1 = off[s.c1];
-        DR_CUDA(ctx, cudaMemcpyAsync(h_out + s0, s.raw.p, (s1 - s0) * 2, cudaMemcpyDeviceToHost, ctx->s_out));
+        bool landed = false;
+        { int r2 = d2h(ctx, h_out + s0, s.raw.p, (s1 - s0) * 2, ctx->s_out, &landed); if (r2) return r2; }
         DR_CUDA(ctx, cudaEventRecord(s.ev_out, ctx->s_out));
         return DRICE_OK;
     };
@@ -921,7 +1095,7 @@ extern "C" int drice_decode_batch_host(drice_ctx *ctx, const void *h_comp, const
             DR_CUDA(ctx, s.raw.reserve((s1 - s0) * 2 + 64));
             DR_CUDA(ctx, s.comp.reserve((b1 - b0) + 64));
             if ((rc = slot_offs_reserve(ctx, s, 1))) break;
-            DR_CUDA(ctx, cudaMemcpyAsync(s.comp.p, (const char *)h_comp + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->s_in));
+            if ((rc = h2d(ctx, s.comp.p, (const char *)h_comp + b0, b1 - b0, ctx->s_in))) break;
             DR_CUDA(ctx, cudaEventRecord(s.ev_in, ctx->s_in));
             DR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_in, 0));
             uint32_t *d_status = (uint32_t *)s.offs.p;
