@@ -149,12 +149,25 @@ def run_reference(args):
     kind = "reference" if O.ref_available("ser" if serial else "omp") else "port"
     if kind == "port":
         O.lib()
-    if serial:
-        os.environ["OMP_NUM_THREADS"] = "1"
-    cores = 1 if serial else len(os.sched_getaffinity(0))
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the all-core arm must not inherit it.  The
+    # variable is set before the OpenMP runtime is loaded AND the team size is set through the
+    # runtime's own API afterwards; `cores` is what omp_get_max_threads() then reports.
+    want = 1 if serial else len(os.sched_getaffinity(0))
+    os.environ["OMP_NUM_THREADS"] = str(want)
     chunks, L, M = _ref_sample(args.workload, args.ref_chunks)
     raw = sum(c.nbytes for c in chunks)
     rr = _RefRunner(kind)
+    (O.ref_lib("ser" if serial else "omp") if kind == "reference" else O.lib())
+    cores = want
+    try:
+        gomp = C.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(C.c_int(want))
+        gomp.omp_get_max_threads.restype = C.c_int
+        cores = int(gomp.omp_get_max_threads())
+    except OSError:
+        pass
+    if serial:
+        cores = 1
     for _ in range(args.warmup):
         rr.step(chunks, L, M, serial)
     te = td = 0.0

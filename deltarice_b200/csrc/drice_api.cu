@@ -68,6 +68,13 @@ struct drice_ctx {
     DevBuf d_filt;                       // generic filter: pre-filtered samples of the batch
     DevBuf d_lane;                       // lane-per-wave encoder: one worst-case slot per wave
     DevBuf d_scan;                       // locate by scanning: per-tile header candidates
+    // segment encoder: the largest record (words) of recent batches sizes the per-wave staging of the
+    // next one.  The kernel raises d_hint[0]; the next call's prep kernel moves it to h_hint (mapped
+    // pinned memory, read by the host without a synchronisation) and clears it.
+    uint32_t *d_hint = nullptr;
+    volatile uint32_t *h_hint = nullptr;
+    uint32_t hint_wave = 0;              // wave length / Rice parameter the hint was measured on
+    int hint_k = -1;
     // pageable caller buffers: two pinned pieces the copies are staged through (see staged_h2d)
     char *h_piece[2] = {nullptr, nullptr};
     cudaEvent_t ev_piece[2] = {nullptr, nullptr};
@@ -183,19 +190,24 @@ int small_copy(drice_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStr
 
 // one launch prepares a call: the tables come over from mapped host memory, the scratch range the
 // kernels expect zeroed (tickets, look-back words) is cleared, the status word reset
-__global__ void prep_kernel(uint32_t *dst, const uint32_t *src, uint32_t nwords, uint4 *zero, size_t zero_vec, uint32_t *status)
+__global__ void prep_kernel(uint32_t *dst, const uint32_t *src, uint32_t nwords, uint4 *zero, size_t zero_vec, uint32_t *status,
+                            uint32_t *hint_dev, volatile uint32_t *hint_host)
 {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
     for (size_t i = tid; i < nwords; i += nth) dst[i] = src[i];
     for (size_t i = tid; i < zero_vec; i += nth) zero[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0 && status) *status = 0;
+    if (tid == 0 && hint_dev) {                      // the previous batch's largest record -> host
+        const uint32_t h = hint_dev[0];
+        if (h) { hint_host[0] = h; hint_host[1] = hint_dev[1]; hint_host[2] = hint_dev[2]; hint_dev[0] = 0; hint_dev[1] = 0; hint_dev[2] = 0; }
+    }
 }
 
 // uploads [chunk_sample_off u64 (n+1)] [second u64 table (n+1), optional] [wave_off u32 (n+1)], zeroes
 // `zero_bytes` (rounded up to 16) at `zero_p` (16-byte aligned, may be null) and resets *status
 int upload_tables(drice_ctx *ctx, const uint64_t *t0, const uint64_t *t1, const uint32_t *wave_off,
                   size_t nchunks, cudaStream_t st, uint64_t **d_t0, uint64_t **d_t1, uint32_t **d_w,
-                  void *zero_p, size_t zero_bytes, uint32_t *status)
+                  void *zero_p, size_t zero_bytes, uint32_t *status, bool with_hint = false)
 {
     const size_t n1 = nchunks + 1;
     const size_t bytes = n1 * 8 * 2 + n1 * 4;
@@ -223,7 +235,8 @@ int upload_tables(drice_ctx *ctx, const uint64_t *t0, const uint64_t *t1, const 
         size_t work = std::max<size_t>(bytes / 4, zero_vec);
         unsigned grid = (unsigned)std::min<size_t>((work + 255) / 256, 296);
         if (grid < 1) grid = 1;
-        prep_kernel<<<grid, 256, 0, st>>>((uint32_t *)ctx->d_tab.p, (const uint32_t *)h, (uint32_t)(bytes / 4), (uint4 *)zero_p, zero_vec, status);
+        prep_kernel<<<grid, 256, 0, st>>>((uint32_t *)ctx->d_tab.p, (const uint32_t *)h, (uint32_t)(bytes / 4), (uint4 *)zero_p, zero_vec, status,
+                                          with_hint ? ctx->d_hint : nullptr, with_hint ? ctx->h_hint : nullptr);
         DR_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
     }
@@ -380,7 +393,10 @@ extern "C" int drice_create(drice_ctx **out, int device)
     ctx->device = device;
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
               copy_streams(device, &ctx->s_in, &ctx->s_out) &&
-              cudaEventCreateWithFlags(&ctx->ev_tab, cudaEventDisableTiming) == cudaSuccess;
+              cudaEventCreateWithFlags(&ctx->ev_tab, cudaEventDisableTiming) == cudaSuccess &&
+              cudaMalloc((void **)&ctx->d_hint, 16) == cudaSuccess && cudaMemset(ctx->d_hint, 0, 16) == cudaSuccess &&
+              cudaMallocHost((void **)&ctx->h_hint, 16) == cudaSuccess;
+    if (ok) ctx->h_hint[0] = ctx->h_hint[1] = 0;
     for (Slot &s : ctx->slots)
         ok = ok && cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming) == cudaSuccess &&
@@ -414,6 +430,8 @@ extern "C" void drice_destroy(drice_ctx *ctx)
         if (ctx->ev_piece[i]) cudaEventDestroy(ctx->ev_piece[i]);
     }
     if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
+    if (ctx->d_hint) cudaFree(ctx->d_hint);
+    if (ctx->h_hint) cudaFreeHost((void *)ctx->h_hint);
     if (ctx->h_sync) cudaFreeHost(ctx->h_sync);
     if (ctx->ev_tab) cudaEventDestroy(ctx->ev_tab);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -525,7 +543,7 @@ extern "C" int drice_encode_batch_dev_async(drice_ctx *ctx, const int16_t *d_raw
     uint64_t *d_soff, *d_unused;
     uint32_t *d_woff;
     rc = upload_tables(ctx, off, nullptr, g.wave_off.data(), nchunks, st, &d_soff, &d_unused, &d_woff,
-                       ctx->d_scratch.p, zeroed, d_status);
+                       ctx->d_scratch.p, zeroed, d_status, true);
     if (rc) return rc;
 
     const int16_t *src = d_raw;
@@ -549,6 +567,18 @@ extern "C" int drice_encode_batch_dev_async(drice_ctx *ctx, const int16_t *d_raw
     p.raw = src;
     EncodeMode md{};
     md.delta = ctx->filter_mode == 0;
+    // the hint is the largest record in WORDS of a recent batch; it only transfers to waves of the same length
+    if (ctx->hint_wave != g.max_wave || ctx->hint_k != k) ctx->h_hint[0] = ctx->h_hint[1] = 0;
+    md.seg_words_hint = ctx->h_hint[0];
+    md.seg_lane_hint = ctx->h_hint[1];
+    ctx->hint_wave = g.max_wave;
+    ctx->hint_k = k;
+    md.seg_max_words = ctx->d_hint;
+    {
+        static const bool debug = getenv("DRICE_DEBUG") != nullptr;
+        if (debug) fprintf(stderr, "[drice] previous batch: largest record %u words, longest lane stream %u words, %u waves packed in place\n",
+                           ctx->h_hint[0], ctx->h_hint[1], ctx->h_hint[2]);
+    }
     p.raw_samples = off[nchunks];
     p.out = d_out;
     p.out_cap_words = out_cap_bytes / 4;

@@ -79,38 +79,7 @@ constexpr int      kLocStages    = 4;
 constexpr uint32_t kLocRingWords = kLocTileWords * kLocStages;
 constexpr uint64_t kLocDirectL   = 32768;
 
-__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t mbar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t mbar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, P1;\n"
-        "}\n" : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
-{
-    while (!mbar_try_wait(mbar, parity)) { }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
-}
+// (mbarrier / bulk-copy wrappers: drice_kernels.cuh)
 
 // issues the tile of words [A, A + kLocTileWords) into the stage at shared address `dst`
 // ((comp + A) is 16-byte aligned; A may be negative by up to 3 words when comp itself is not):

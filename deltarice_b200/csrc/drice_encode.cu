@@ -33,7 +33,9 @@
 // packing sweep that re-reads the wave and streams completed words straight to HBM.
 #include "drice_kernels.cuh"
 
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 namespace drice {
 
@@ -978,6 +980,537 @@ encode_lane_kernel(const EncodeParams p, uint32_t *const scratch, const uint32_t
 }
 
 // ======================================================================================
+// segment kernel: one WARP per wave, one LANE per contiguous SEGMENT (the default encoder)
+// ======================================================================================
+// The codec is bound by the integer pipes, not by HBM: on sm_100 the ALU pipe (LOP3 / SHF / PRMT /
+// IADD3) and the FMA pipe (IMAD, VIADD.16x2) each take one warp instruction per two cycles per SM
+// sub-partition and IMAD.WIDE / IMAD.HI one per four (tools/ubench_pipes.cu), so the kernel is
+// designed around pipe cycles per sample and around keeping many warps resident:
+//   * a wave is cut into BLOCKS of 16 samples = one 32-byte sector, counted from the 32-byte aligned
+//     address below the wave; a PIECE (<= 32 x nbmax blocks, normally the whole wave) deals its
+//     blocks evenly to the lanes as contiguous segments (the first lanes get one block more).  A lane
+//     reads its segment sector by sector straight into registers (ld.global.nc.v8, two sectors
+//     ahead): no shared-memory staging of the input, full sectors only, and the only irregular
+//     blocks of a wave are its first (the samples in front of the wave are zeroed: they then code as
+//     K+1 known bits each, which are skipped) and its last (padded with repeats of the last sample:
+//     zero deltas, cut off again);
+//   * every lane Rice-codes its segment sequentially into a private bit stream in shared memory
+//     ([word][lane] rings: conflict free) - no per-round warp scan, no stitching inside the loop.
+//     Two samples become one pair code with IMAD.WIDE (the multiply is the shift), appended to a
+//     64-bit window with one more IMAD.WIDE; the word under construction is stored unconditionally
+//     (a complete word overwrites the partial one), so the loop has no branch;
+//   * after the piece ONE warp scan of the lanes' bit counts gives every segment its bit offset in
+//     the wave and each lane funnel-shifts its stream into the wave's staging (boundary words are
+//     stitched with one shuffle);
+//   * tiles of NW waves, the control warp's decoupled look-back and the deferred coalesced copy-out
+//     are those of the tile kernel, without its per-iteration barrier among the workers.
+// A wave that outgrows its staging (or a lane its ring) is packed straight into its record by
+// encode_wave<.., true>.
+constexpr int      kSegMaxWorkers = 10;       // worker warps per CTA (+ 1 control warp); two CTAs per SM
+constexpr uint32_t kSegMinL       = 1024;     // shorter waves: tile kernel (lanes would idle)
+constexpr uint32_t kSegMaxBlocks  = 8;        // blocks per lane and piece
+
+struct SegLaunch {
+    uint32_t nworkers;      // worker warps per CTA (+ 1 control warp)
+    uint32_t nbmax;         // blocks (of 16 samples) per lane and piece, <= kSegMaxBlocks
+    uint32_t lane_words;    // words of one lane's private stream ring: a power of two
+    uint32_t stage_words;   // words of a wave's merged stream (nstage buffers per worker)
+    uint32_t nstage;        // 2 or 3: a wave is copied out nstage - 1 iterations after it was encoded
+    uint32_t ntiles;
+    uint32_t *max_words;    // hints for the next call (may be null): [0] largest record, [1] largest lane stream (words)
+    // multiplier constants of the inner loop, passed as PARAMETERS: a power of two the compiler can
+    // see is strength-reduced to shifts, i.e. moved from the FMA pipe back to the busier ALU pipe
+    uint32_t mulx;          // 0xFFFF0001: w * mulx has hi(w) - lo(w) in its high half
+    uint32_t p16;           // 2^16
+    uint32_t p16mk;         // 2^(16-K)
+    uint32_t four;          // 4
+    uint32_t dbg;           // DRICE_ENC_SEG_DBG (timing experiments only; output is wrong when set)
+    long long *trace;       // DRICE_ENC_SEG_TRACE: clock64 stamps of CTA 0 (diagnostics), else null
+};
+
+__device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c)
+{
+    uint64_t d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+// (a ^ b) & c and (a ^ b) & ~c in one LOP3 each; (a & b) | c
+__device__ __forceinline__ uint32_t xor_and(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t xor_andn(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x14;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+struct SegPacker {
+    uint32_t acc;       // pending bits in the low (b & 31) bits, stale above
+    uint32_t b;         // bits produced so far in this piece
+    uint32_t base;      // shared address of the lane's ring word 0 (the ring block is aligned to its size)
+    uint32_t wmask;     // (lane_words - 1) << 7: byte offset of a ring word
+    // appends a code of `len` <= 30 bits given as two disjoint bit fields v0 | v1 (P = 2^len).  The
+    // word under construction is stored every time: if the code completes it the store is final,
+    // otherwise a later store overwrites it.  (The fields are joined with a three-input OR, not an
+    // add, so that they cannot be folded into the multiply as a 64-bit addend.)
+    __device__ __forceinline__ void append(uint32_t v0, uint32_t v1, uint32_t P, uint32_t len, const SegLaunch &c)
+    {
+        const uint64_t a = mad_wide(acc, P, 0ull);
+        const uint32_t alo = (uint32_t)a | v0 | v1;          // the low `len` bits of the product are 0
+        const uint32_t at = and_or(b * c.four, wmask, base); // word b >> 5 of the ring
+        b += len;
+        sts32(at, __funnelshift_r(alo, (uint32_t)(a >> 32), b));
+        acc = alo;
+    }
+};
+
+// two samples (both quotients < 8) as one code: VL = packed remainders, QK = packed quotient * M.
+template <int K>
+__device__ __forceinline__ void seg_put_pair(SegPacker &pk, uint32_t VL, uint32_t QK, const SegLaunch &c)
+{
+    const uint64_t qs = mad_wide(QK, c.p16mk, 0ull);                         // {q_hi, q_lo << 16}
+    const uint32_t q_hi = (uint32_t)(qs >> 32);
+    const uint32_t S = ((uint32_t)qs >> 16) + q_hi;                           // q_lo + q_hi (one LEA.HI)
+    const uint32_t Ph = __funnelshift_l(0u, (2u << K) << 16, q_hi);           // 2^(16 + len_hi)
+    // terminator bits: VIADD.16x2 (FMA pipe); the halves cannot carry (r < M)
+    const uint64_t sp = mad_wide(__vadd2(VL, RiceConst<K>::MM), c.p16, 0ull); // {r_hi + M, (r_lo + M) << 16}
+    const uint64_t t = mad_wide((uint32_t)sp, Ph, 0ull);                      // high word: (r_lo + M) * 2^len_hi
+    const uint32_t P = __funnelshift_l(0u, 1u << (2 * K + 2), S);
+    pk.append((uint32_t)(t >> 32), (uint32_t)(sp >> 32), P, S + (2u * K + 2u), c);
+}
+template <int K>
+__device__ __forceinline__ void seg_put_single(SegPacker &pk, uint32_t u, const SegLaunch &c)
+{
+    uint32_t v, l;
+    rice_code<K>(u, v, l);
+    pk.append(v, 0u, pow2(l), l, c);
+}
+
+// 8 samples = 4 packed words of one lane.  pw = the word before them (previous sample in its high half).
+template <int K, bool kDelta>
+__device__ __forceinline__ void seg_block(SegPacker &pk, const uint32_t (&w)[4], uint32_t &pw, const SegLaunch &c)
+{
+    using C = RiceConst<K>;
+    constexpr uint32_t LOW = ((1u << K) - 1u) * 0x10001u;
+    uint32_t VL[4], QK[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        // delta + zig-zag on packed halves (src/deltaRice.c:57-62, :207-211)
+        uint32_t D = w[m];
+        if (kDelta) {
+            const uint32_t prev = m ? w[m - 1] : pw;
+            const uint32_t X = w[m] * c.mulx;                // high half: hi(w) - lo(w)
+            const uint32_t Y = w[m] - (prev >> 16);          // low half:  lo(w) - hi(prev)
+            D = prmt(Y, X, 0x7610);
+        }
+        const uint32_t D2 = __vadd2(D, D), Sg = prmt(D, 0, 0xbb99);    // U = D2 ^ Sg
+        VL[m] = xor_and(D2, Sg, LOW);
+        QK[m] = xor_andn(D2, Sg, LOW);
+    }
+    pw = w[3];
+    if constexpr (C::kPairs) {
+        const bool esc = (((QK[0] | QK[1]) | (QK[2] | QK[3])) & C::HM) != 0u;
+        if (!__any_sync(__activemask(), esc)) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) seg_put_pair<K>(pk, VL[m], QK[m], c);
+        } else {                                    // some lane holds a quotient >= 8 (escape code)
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                if (__any_sync(__activemask(), (QK[m] & C::HM) != 0u)) {
+                    const uint32_t U = VL[m] | QK[m];
+                    seg_put_single<K>(pk, U & 0xFFFFu, c);
+                    seg_put_single<K>(pk, U >> 16, c);
+                } else {
+                    seg_put_pair<K>(pk, VL[m], QK[m], c);
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const uint32_t U = VL[m] | QK[m];
+            seg_put_single<K>(pk, U & 0xFFFFu, c);
+            seg_put_single<K>(pk, U >> 16, c);
+        }
+    }
+}
+
+// block B (16 samples from origin + 32 B) of a wave.  Only the wave's first and last block can be ragged
+// (samples in front of the wave / behind it inside the 32-byte sector): those two sectors are patched
+// once per wave into a 64-byte scratch of the warp in shared memory (seg_patch) and read from there.
+__device__ __forceinline__ Sector lds_sector(uint32_t addr)
+{
+    Sector r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "r"(addr));
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ Sector seg_load(const unsigned char *origin, uint32_t B, uint32_t NB, bool lead, bool tail, uint32_t scratch)
+{
+    if ((B == 0u && lead) || (B + 1u == NB && tail)) return lds_sector(scratch + (B == 0u && lead ? 0u : 32u));
+    return ldg_sector(origin + (size_t)B * 32u);
+}
+// lanes 0..15: the 16 samples of the wave's first sector, lanes 16..31: of its last sector.  Samples in front
+// of the wave become 0, samples behind it repeat the last one (`fill`); nothing outside the wave is read.
+__device__ __forceinline__ void seg_patch(const unsigned char *origin, uint32_t NB, uint32_t mis, uint32_t span, uint32_t fill,
+                                          uint32_t scratch, int lane)
+{
+    const uint32_t idx = (lane < 16 ? 0u : (NB - 1u) * 16u) + ((uint32_t)lane & 15u);
+    uint32_t v = idx < mis ? 0u : fill;
+    if (idx >= mis && idx < span) v = *reinterpret_cast<const uint16_t *>(origin + (size_t)idx * 2u);
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(scratch + (uint32_t)lane * 2u), "h"((uint16_t)v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// the rare wave that outgrew its staging: out of line, so that it stays out of the instruction cache
+template <int K, bool kDelta>
+__device__ __noinline__ void encode_wave_in_place(const int16_t *wave, uint32_t n, const int16_t *raw_hi, int lane, uint32_t *dst, uint32_t cap)
+{
+    bool dummy;
+    encode_wave<K, true, kDelta>(wave, n, raw_hi, lane, dst, cap, &dummy);
+}
+
+// Shared control state of a CTA lives in a ring of kSegRing slots (iteration % kSegRing).  There is no
+// barrier among the workers.  A wave is copied out D = nstage - 1 iterations after it was encoded (the
+// merged stream waits in one of the worker's nstage staging buffers), when the control warp has long
+// resolved its tile's offset: a worker needs the offset of tile it-D to finish iteration it, and the
+// control warp needs every worker's size of that tile, so no worker is ever more than D+1 iterations
+// ahead of another and six slots are never reused too early.
+// The worker that COMPLETES tile it (the last to report its wave's size) claims the tile of iteration
+// it+2: tiles complete in ticket order machine-wide (a tile is claimed two iterations of its CTA's
+// slowest worker before it completes), so a look-back finds its predecessors published, and every
+// worker knows its next wave one iteration early: it prefetches that wave into L2 while it encodes.
+constexpr int kSegRing = 6;
+
+struct SegDeferred {                       // what the copy-out of a wave needs, parked in shared memory
+    uint64_t begin;
+    uint32_t n, chunk, chunk_total, nwords, flags;   // flags: 1 first, 2 have, 4 overflow
+    uint32_t pad_;
+};
+
+template <int K, bool kDelta>
+__global__ void __launch_bounds__((kSegMaxWorkers + 1) * 32, 2)
+encode_seg_kernel(const EncodeParams p, const SegLaunch sl)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ uint32_t s_tile[8];                        // tile of iteration it (ring of 8)
+    __shared__ volatile uint32_t s_tag[8];                // = it + 1 once s_tile[it & 7] is valid
+    __shared__ uint32_t s_mine[kSegRing][kSegMaxWorkers]; // words each wave contributes
+    __shared__ uint32_t s_cnt[kSegRing];
+    __shared__ uint32_t s_total[kSegRing];
+    __shared__ uint64_t s_off[kSegRing];
+    __shared__ volatile uint32_t s_flag[kSegRing];        // = it + 1 once s_off is valid
+    __shared__ SegDeferred s_def[kSegMaxWorkers][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int NW = (int)sl.nworkers;
+    const bool control = warp == NW;
+    const uint32_t ntiles = sl.ntiles;
+    const uint32_t D = sl.nstage - 1u;                    // iterations between encoding a wave and copying it out
+
+    if (threadIdx.x < kSegRing) { s_flag[threadIdx.x] = 0; s_cnt[threadIdx.x] = 0; }
+    if (threadIdx.x < 8) s_tag[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_tile[0] = atomicAdd(p.ticket, 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_tile[1] = atomicAdd(p.ticket, 1u);              // (after the machine's first round of claims, roughly)
+        s_tag[0] = 1;
+        s_tag[1] = 2;
+    }
+    __syncthreads();
+
+    if (control) {
+        for (uint32_t it = 0;; ++it) {
+            const int slot = it % kSegRing;
+            // sleeps on a named barrier (one per ring slot) until the tile's last worker arrives
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + slot) : "memory");
+            const uint32_t tile = s_tile[it & 7];
+            if (tile >= ntiles) break;
+            const uint64_t mine = s_total[slot];
+            const uint64_t excl = lookback_excl(p.lookback, tile, mine, lane);
+            if (lane == 0) {
+                s_off[slot] = excl;
+                __threadfence_block();
+                s_flag[slot] = it + 1;
+                if (excl + mine > p.out_cap_words) atomicOr(p.status, kErrCapacity);
+                if (tile == ntiles - 1) p.chunk_byte_off[p.nchunks] = (excl + mine) * 4;
+            }
+            __syncwarp();
+        }
+        return;
+    }
+
+    // ---- workers ---------------------------------------------------------------------------
+    const uint32_t stage_words = sl.stage_words;
+    const uint32_t ring_bytes = sl.lane_words * 128u;                          // one warp's 32 lane rings
+    const uint32_t dyn = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t rings0 = (dyn + ring_bytes - 1u) & ~(ring_bytes - 1u);      // ring blocks are aligned to their size
+    const uint32_t stage_s0 = rings0 + (uint32_t)NW * ring_bytes + (uint32_t)warp * (sl.nstage * stage_words * 4u + 64u);
+    const uint32_t scratch = stage_s0 + sl.nstage * stage_words * 4u;         // the wave's ragged first / last sector
+    const int16_t *const raw_hi = p.raw + p.raw_samples;
+    SegPacker pk;
+    pk.base = rings0 + (uint32_t)warp * ring_bytes + (uint32_t)lane * 4u;
+    pk.wmask = (sl.lane_words - 1u) << 7;
+    const uint32_t ring_bits = (sl.lane_words - 1u) * 32u;                     // a lane past this has overflowed
+
+    uint32_t maxw = 0, maxlane = 0, novf = 0;
+    uint32_t buf = 0;                                    // staging buffer of this iteration: it % nstage
+    for (uint32_t it = 0;; ++it) {
+        const int slot = it % kSegRing;
+        const bool tr = sl.trace && blockIdx.x == 0 && it >= 8u && it < 24u;
+        long long *const trp = sl.trace + ((size_t)warp * 16u + (it - 8u)) * 8u;
+#define SEG_STAMP(k) do { if (tr && lane == 0) trp[k] = clock64(); } while (0)
+        SEG_STAMP(0);
+        while (s_tag[it & 7] != it + 1) __nanosleep(20);     // (claimed when tile it-2 completed: long ago)
+        __threadfence_block();
+        const uint32_t tile = s_tile[it & 7];
+        const bool live = tile < ntiles;
+        SegDeferred df;
+        df.begin = 0; df.n = 0; df.chunk = 0; df.chunk_total = 0; df.nwords = 0; df.flags = 0; df.pad_ = 0;
+        if (live) {
+            const uint32_t g = tile * (uint32_t)NW + (uint32_t)warp;
+            uint32_t mine = 0;
+            if (g < p.nwaves) {
+                const WaveGeom wg = locate_wave(p, g);
+
+                df.begin = wg.begin; df.n = wg.n; df.chunk = wg.chunk; df.chunk_total = wg.chunk_total;
+                df.flags = 2u | wg.first;
+                bool ovf = false;
+                uint32_t nwords = 0;
+                if (wg.chunk_total) {
+                    const uintptr_t wa = reinterpret_cast<uintptr_t>(p.raw + wg.begin);
+                    const unsigned char *const origin = reinterpret_cast<const unsigned char *>(wa & ~(uintptr_t)31);
+                    const uint32_t mis = (uint32_t)(wa & 31u) >> 1;            // samples between origin and the wave
+                    const uint32_t span = mis + wg.n;
+                    const uint32_t NB = (span + 15u) >> 4;                     // blocks of the wave
+                    SEG_STAMP(1);
+                    const bool lead = mis != 0u, tail = (span & 15u) != 0u;
+                    if (lead || tail) {
+                        uint32_t fill = 0;
+                        if (kDelta && tail) fill = (uint32_t)(uint16_t)p.raw[wg.begin + wg.n - 1u];
+                        seg_patch(origin, NB, mis, span, fill, scratch, lane);
+                        __syncwarp();
+                    }
+                    const uint32_t stage_s = stage_s0 + buf * stage_words * 4u;
+                    uint32_t Bw = 0;                 // bits of the wave merged so far
+                    uint32_t carry = 0;              // the wave's last, still partial word (left aligned)
+                    for (uint32_t blk0 = 0; blk0 < NB; blk0 += 32u * sl.nbmax) {
+                        // ---- this lane's segment of the piece: blocks [start, start + mb) ------------------
+                        const uint32_t pnb = NB - blk0 < 32u * sl.nbmax ? NB - blk0 : 32u * sl.nbmax;
+                        const uint32_t q = pnb >> 5, r = pnb & 31u;
+                        const uint32_t mb = q + ((uint32_t)lane < r ? 1u : 0u);
+                        const uint32_t start = blk0 + q * (uint32_t)lane + ((uint32_t)lane < r ? (uint32_t)lane : r);
+                        const uint32_t nact = q ? 32u : r;                        // lanes that hold blocks
+                        pk.acc = 0;
+                        pk.b = 0;
+                        if (mb) {
+                            uint32_t pw = 0;
+                            if (kDelta && start) pw = (uint32_t)*reinterpret_cast<const uint16_t *>(origin + (size_t)start * 32u - 2u) << 16;
+                            Sector c0 = seg_load(origin, start, NB, lead, tail, scratch), c1 = c0, c2 = c0;
+                            if (mb > 1u) c1 = seg_load(origin, start + 1u, NB, lead, tail, scratch);
+                            if (mb > 2u) c2 = seg_load(origin, start + 2u, NB, lead, tail, scratch);
+                            if (tr && lane == 0) { trp[2] = clock64(); trp[7] = (long long)(c0.w[0] & 1u) + clock64(); }
+                            for (uint32_t bl = 0; bl < mb; ++bl) {
+                                Sector cur = c0;
+                                c0 = c1;
+                                c1 = c2;
+                                if (bl + 3u < mb) c2 = seg_load(origin, start + bl + 3u, NB, lead, tail, scratch);
+#pragma unroll 1
+                                for (int half = 0; half < 2; ++half) {           // (one copy of the code: it has to stay in the instruction cache)
+                                    const uint32_t w4[4] = {cur.w[0], cur.w[1], cur.w[2], cur.w[3]};
+                                    seg_block<K, kDelta>(pk, w4, pw, sl);
+                                    cur.w[0] = cur.w[4]; cur.w[1] = cur.w[5]; cur.w[2] = cur.w[6]; cur.w[3] = cur.w[7];
+                                }
+                            }
+                            if (pk.b & 31u) {
+                                uint32_t last;
+                                asm("shl.b32 %0, %1, %2;" : "=r"(last) : "r"(pk.acc), "r"(32u - (pk.b & 31u)));
+                                sts32(and_or(pk.b << 2, pk.wmask, pk.base), last);
+                            }
+                        }
+                        __syncwarp();
+                        SEG_STAMP(3);
+                        maxlane = pk.b > maxlane ? pk.b : maxlane;
+                        // ---- bit offsets of the segments in the wave ---------------------------------------
+                        const uint32_t skip = (start == 0u && mb) ? mis * (K + 1u) : 0u;    // the zeroed samples in front
+                        uint32_t nbits = 0;
+                        if (mb) {
+                            nbits = pk.b - skip;
+                            if (start + mb == NB) nbits -= (NB * 16u - span) * (K + 1u);  // the repeats behind the wave
+                        }
+                        uint32_t inc = nbits;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+                            if (lane >= d) inc += t;
+                        }
+                        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+                        const uint32_t dbit = Bw + inc - nbits;                  // first bit of this lane's segment
+                        // every segment but the last holds >= 32 bits (a word then has at most two contributors)
+                        // and no lane has run around its ring
+                        const bool shape_ok = __all_sync(0xffffffffu, pk.b <= ring_bits && (!mb || (uint32_t)lane + 1u >= nact || nbits >= 32u));
+                        if (!shape_ok || ((Bw + total + 31u) >> 5) + 1u > stage_words) ovf = true;
+                        if (!ovf && !(sl.dbg & 1u)) {
+                            // ---- merge: funnel-shift the lane's stream to its place ------------------------
+                            uint32_t out_frag = 0, head = 0, last = 0;
+                            const uint32_t ebit = dbit + nbits;
+                            const uint32_t j0 = dbit >> 5, j1 = (ebit - 1u) >> 5;
+                            const bool tail_partial = (ebit & 31u) != 0u;
+                            const bool single = j0 == j1;
+                            const int32_t t = (int32_t)skip - (int32_t)dbit;
+                            const uint32_t tr = (uint32_t)t & 31u;
+                            const int32_t m0 = (int32_t)j0 + (t >> 5);           // stream word under stage word j0
+                            uint32_t pa = pk.base + (uint32_t)(m0 + 1) * 128u;    // address of stream word m0 + 1
+                            uint32_t sa = stage_s + j0 * 4u;
+                            if (nbits) {
+                                const uint32_t tmask = tail_partial ? ~(0xFFFFFFFFu >> (ebit & 31u)) : 0xFFFFFFFFu;
+                                uint32_t cur = m0 >= 0 ? lds32(pa - 128u) : 0u;
+                                uint32_t nx = lds32(pa);
+                                head = __funnelshift_l(nx, cur, tr) & (0xFFFFFFFFu >> (dbit & 31u));
+                                if (single) head &= tmask;
+                                uint32_t left = j1 - j0;                          // words after the first
+                                while (left > 4u) {                               // four words per step
+                                    const uint32_t a1 = lds32(pa + 128u), a2 = lds32(pa + 256u), a3 = lds32(pa + 384u), a4 = lds32(pa + 512u);
+                                    sts32(sa + 4u, __funnelshift_l(a1, nx, tr));
+                                    sts32(sa + 8u, __funnelshift_l(a2, a1, tr));
+                                    sts32(sa + 12u, __funnelshift_l(a3, a2, tr));
+                                    sts32(sa + 16u, __funnelshift_l(a4, a3, tr));
+                                    nx = a4;
+                                    pa += 512u;
+                                    sa += 16u;
+                                    left -= 4u;
+                                }
+                                while (left) {
+                                    cur = nx;
+                                    pa += 128u;
+                                    sa += 4u;
+                                    nx = lds32(pa);
+                                    const uint32_t f = __funnelshift_l(nx, cur, tr);
+                                    if (--left) sts32(sa, f); else last = f & tmask;
+                                }
+                                if (tail_partial && !single) out_frag = last;
+                            }
+                            uint32_t in_frag = __shfl_up_sync(0xffffffffu, out_frag, 1);
+                            if (lane == 0) in_frag = carry;
+                            if (nbits) {
+                                const uint32_t w0 = head | in_frag;
+                                if (single) {
+                                    if (tail_partial) out_frag = w0; else sts32(stage_s + j0 * 4u, w0);
+                                } else {
+                                    sts32(stage_s + j0 * 4u, w0);
+                                    if (!tail_partial) sts32(stage_s + j1 * 4u, last);
+                                }
+                            }
+                            carry = __shfl_sync(0xffffffffu, out_frag, (int)nact - 1);
+                        }
+                        Bw += total;
+                        __syncwarp();
+                    }
+                    SEG_STAMP(4);
+                    if (!ovf && (Bw & 31u) && lane == 0) sts32(stage_s + (Bw >> 5) * 4u, carry);
+                    nwords = (Bw + 31u) >> 5;
+                    mine = nwords + 1u;
+                    maxw = nwords > maxw ? nwords : maxw;
+                    __syncwarp();
+                }
+                df.nwords = nwords;
+                if (ovf) { df.flags |= 4u; ++novf; }
+                mine += wg.first;                            // empty chunk: header only
+            }
+            bool last = false;
+            if (lane == 0) {
+                s_mine[slot][warp] = mine;
+                __threadfence_block();
+                if (atomicAdd(&s_cnt[slot], 1u) == (uint32_t)NW - 1u) {
+                    // last worker of the tile: publish the tile's aggregate, claim the tile of iteration it + 2
+                    __threadfence_block();
+                    uint32_t total = 0;
+                    for (int w = 0; w < NW; ++w) total += s_mine[slot][w];
+                    st_relaxed_u64(p.lookback + tile, kFlagAggregate | (uint64_t)total);
+                    s_total[slot] = total;
+                    s_cnt[slot] = 0;
+                    s_tile[(it + 2) & 7] = atomicAdd(p.ticket, 1u);
+                    __threadfence_block();
+                    s_tag[(it + 2) & 7] = it + 3;
+                    last = true;
+                }
+            }
+            if (__shfl_sync(0xffffffffu, last, 0))           // wakes the control warp
+                asm volatile("bar.arrive %0, 64;" ::"r"(2 + slot) : "memory");
+        } else if (warp == 0) {
+            __threadfence_block();
+            asm volatile("bar.arrive %0, 64;" ::"r"(2 + slot) : "memory");   // lets the control warp see the end
+        }
+        if (lane == 0) s_def[warp][buf] = df;
+        __syncwarp();
+        SEG_STAMP(5);
+        // ---- copy out the wave(s) encoded D iterations ago (all that are left once the tiles have run out) ----
+        for (uint32_t back = D; back >= (live ? D : 1u); --back) {
+            if (it < back) continue;
+            const uint32_t jt = it - back;                       // iteration whose wave goes out
+            const uint32_t jb = jt % sl.nstage;
+            const SegDeferred d = s_def[warp][jb];
+            if (!(d.flags & 2u)) continue;
+            const int psl = jt % kSegRing;
+            while (s_flag[psl] != jt + 1) __nanosleep(400);      // tile offset: normally there long ago
+            __threadfence_block();
+            const uint32_t v = lane < NW ? s_mine[psl][lane] : 0u;
+            const uint32_t loff = __reduce_add_sync(0xffffffffu, lane < warp ? v : 0u);
+            const uint64_t off = s_off[psl] + loff;
+            const uint32_t first = d.flags & 1u;
+            const uint32_t rec_words = d.chunk_total ? d.nwords + 1u : 0u;
+            const bool fits = off + rec_words + first <= p.out_cap_words;
+            if (lane == 0 && first) p.chunk_byte_off[d.chunk] = off * 4;
+            if (fits) {
+                uint32_t *rec = p.out + off + first;
+                if (lane == 0) {
+                    if (first) p.out[off] = d.chunk_total;
+                    if (rec_words) rec[0] = d.nwords;
+                }
+                if (rec_words) {
+                    if (sl.dbg & 2u) {
+                    } else if (!(d.flags & 4u)) {
+                        uint32_t sa = stage_s0 + jb * stage_words * 4u + (uint32_t)lane * 4u;
+                        uint32_t *dst = rec + 1 + lane;
+                        uint32_t i = lane;
+                        for (; i + 96u < d.nwords; i += 128u, sa += 512u, dst += 128) {
+                            const uint32_t a0 = lds32(sa), a1 = lds32(sa + 128u), a2 = lds32(sa + 256u), a3 = lds32(sa + 384u);
+                            dst[0] = a0; dst[32] = a1; dst[64] = a2; dst[96] = a3;
+                        }
+                        for (; i < d.nwords; i += 32u, sa += 128u, dst += 32) *dst = lds32(sa);
+                    } else {                                 // larger than the staging: pack in place
+                        encode_wave_in_place<K, kDelta>(p.raw + d.begin, d.n, raw_hi, lane, rec + 1, d.nwords);
+                    }
+                }
+            }
+            __syncwarp();
+            if (back == 1u) break;
+        }
+        SEG_STAMP(6);
+        if (!live) break;
+        buf = buf + 1u == sl.nstage ? 0u : buf + 1u;
+    }
+    maxlane = __reduce_max_sync(0xffffffffu, maxlane);
+    if (sl.max_words && lane == 0 && maxw) {
+        atomicMax(sl.max_words, maxw);
+        atomicMax(sl.max_words + 1, (maxlane + 31u) >> 5);
+        if (novf) atomicAdd(sl.max_words + 2, novf);      // waves that took the in-place path (diagnostics)
+    }
+}
+
+// ======================================================================================
 // multi-tile kernel (waves longer than one tile): generic per-sample code path
 // ======================================================================================
 __device__ __forceinline__ int4 ld_stream_v4(const int4 *p)
@@ -1219,17 +1752,10 @@ encode_multi_kernel(const EncodeParams p, const int dmask)
     pack_wave_streaming<K>(wave, wg.n, rec, smem, dmask);
 }
 
-int g_num_sms = 0;
-
 template <int K>
 int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len, cudaStream_t st)
 {
-    if (!g_num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
-    }
+    const int g_num_sms = device_sm_count();
     const size_t smem_multi = (size_t)(kEncMaxThreads * 13 + 1 + 2 * kEncMaxThreads + 33 + 3) * sizeof(uint32_t);
     if (max_wave_len > (uint32_t)kEncTileMaxL) {
         encode_multi_kernel<K><<<p.nwaves, kEncMaxThreads, smem_multi, st>>>(p, md.delta ? -1 : 0);
@@ -1237,12 +1763,11 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
     }
     // large batches: one lane per wave (needs a worst-case sized scratch slot per wave)
     if (md.lane_scratch && md.lane_slot_words) {
-        static bool attr_lane = false;
+        static DeviceOnce attr_lane;
         const size_t smem_lane = (size_t)kLaneWarps * kLaneRingWords * 128;
-        if (!attr_lane) {
+        if (attr_lane.first()) {
             cudaFuncSetAttribute(encode_lane_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lane);
             cudaFuncSetAttribute(encode_lane_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            attr_lane = true;
         }
         const uint32_t ngroups = (p.nwaves + 31u) / 32u;
         uint32_t nslices = (max_wave_len / 16u + kLaneSliceBlocks - 1u) / kLaneSliceBlocks;
@@ -1259,6 +1784,97 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
                                                                       md.delta ? 0xFFFF0001u : 1u, md.delta ? 0xFFFFFFFFu : 0u);
         return 1;
     }
+    // the segment kernel: waves of kSegMinL .. kEncTileMaxL samples
+    {
+        static const bool seg_on = [] { const char *e = getenv("DRICE_ENC_SEG"); return e && atoi(e) != 0; }();
+        if (seg_on && max_wave_len >= kSegMinL) {
+            SegLaunch sl{};
+            // blocks of 16 samples per lane and piece: the whole wave in one piece when that needs <= kSegMaxBlocks
+            const uint32_t nb_wave = (max_wave_len + 15u + 15u) / 16u;                 // (+15: misalignment)
+            const uint32_t np = (nb_wave + 32u * kSegMaxBlocks - 1u) / (32u * kSegMaxBlocks);
+            sl.nbmax = ((nb_wave + np - 1u) / np + 31u) / 32u;
+            const uint32_t seg = sl.nbmax * 16u;
+            const uint32_t worst = (25u * max_wave_len + 31u) / 32u + 8u;
+            // words per record: the previous batch's largest (+ margin), else room for 10 bits per sample
+            uint32_t rec = md.seg_words_hint ? md.seg_words_hint + md.seg_words_hint / 16u + 16u
+                                             : (10u * max_wave_len + 31u) / 32u + 16u;
+            static const long stage_env = [] { const char *e = getenv("DRICE_ENC_STAGE_WORDS"); return e ? atol(e) : 0l; }();
+            if (stage_env > 0) rec = (uint32_t)stage_env;
+            if (rec > worst) rec = worst;
+            if (rec < 64u) rec = 64u;
+            sl.stage_words = (rec + 3u) & ~3u;
+            // a lane's ring: the previous batch's longest lane stream (+ margin), else room for 12 bits per
+            // sample; a power of two, at most the worst case of a segment
+            uint32_t lw = 16u;
+            const uint32_t lane_need = md.seg_lane_hint ? md.seg_lane_hint + md.seg_lane_hint / 8u + 3u : (12u * seg) / 32u + 3u;
+            const uint32_t lane_worst = (25u * seg + 31u) / 32u + 2u;
+            while (lw < lane_need && lw < lane_worst) lw <<= 1;
+            sl.lane_words = lw;
+            static const long nstage_env = [] { const char *e = getenv("DRICE_ENC_SEG_STAGES"); return e ? atol(e) : 0l; }();
+            sl.nstage = nstage_env == 2 ? 2u : (nstage_env == 3 ? 3u : (sl.stage_words <= 1024u ? 3u : 2u));
+            const size_t warp_bytes = (size_t)lw * 128u + (size_t)sl.nstage * sl.stage_words * 4u + 64u;
+            const size_t avail = (227u * 1024u) / 2u - 1024u - (size_t)lw * 128u;      // two CTAs per SM; static + alignment slack
+            static const long nw_env = [] { const char *e = getenv("DRICE_ENC_SEG_WARPS"); return e ? atol(e) : 0l; }();
+            uint32_t nw = (uint32_t)(avail / warp_bytes);
+            if (nw > (uint32_t)kSegMaxWorkers) nw = kSegMaxWorkers;
+            if (nw_env > 0 && (uint32_t)nw_env < nw) nw = (uint32_t)nw_env;
+            if (nw >= 2u) {
+                if (nw > p.nwaves) nw = p.nwaves;
+                sl.nworkers = nw;
+                sl.ntiles = (p.nwaves + nw - 1u) / nw;
+                sl.max_words = md.seg_max_words;
+                sl.mulx = 0xFFFF0001u;
+                sl.p16 = 65536u;
+                sl.p16mk = 65536u >> (K <= 7 ? K : 0);
+                sl.four = 4u;
+                static const long dbg_env = [] { const char *e = getenv("DRICE_ENC_SEG_DBG"); return e ? atol(e) : 0l; }();
+                sl.dbg = (uint32_t)dbg_env;
+                static const bool debug = getenv("DRICE_DEBUG") != nullptr;
+                if (debug)
+                    fprintf(stderr, "[drice] encode_seg K=%d L=%u waves=%u: %u workers/CTA, nbmax=%u, lane ring %u words, staging %u x %u words, "
+                                    "hints rec=%u lane=%u, smem %zu B\n", K, max_wave_len, p.nwaves, nw, sl.nbmax, lw, sl.nstage, sl.stage_words,
+                            md.seg_words_hint, md.seg_lane_hint, warp_bytes * nw + (size_t)lw * 128u);
+                const size_t smem = warp_bytes * nw + (size_t)lw * 128u;
+                auto launch_seg = [&](auto kernel, DeviceOnce &once) {
+                    if (once.first()) {
+                        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+                        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+                    }
+                    int occ = 0;
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, (int)(nw + 1u) * 32, smem);
+                    if (occ < 1) occ = 1;
+                    uint32_t grid = (uint32_t)(device_sm_count() * occ);
+                    if (grid > sl.ntiles) grid = sl.ntiles;
+                    kernel<<<grid, (nw + 1u) * 32u, smem, st>>>(p, sl);
+                };
+                static const char *trace_path = getenv("DRICE_ENC_SEG_TRACE");
+                static long long *d_trace = nullptr;
+                const size_t trace_n = (size_t)kSegMaxWorkers * 16u * 8u;
+                if (trace_path && !d_trace) cudaMalloc((void **)&d_trace, trace_n * sizeof(long long));
+                if (trace_path && d_trace) cudaMemsetAsync(d_trace, 0, trace_n * sizeof(long long), st);
+                sl.trace = trace_path ? d_trace : nullptr;
+                static DeviceOnce once_d, once_n;
+                if (md.delta) launch_seg(encode_seg_kernel<K, true>, once_d);
+                else launch_seg(encode_seg_kernel<K, false>, once_n);
+                if (trace_path && d_trace) {                 // diagnostics only: synchronous
+                    std::vector<long long> h(trace_n);
+                    cudaStreamSynchronize(st);
+                    cudaMemcpy(h.data(), d_trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost);
+                    if (FILE *f = fopen(trace_path, "w")) {
+                        for (size_t w = 0; w < (size_t)nw; ++w)
+                            for (size_t i = 0; i < 16; ++i) {
+                                const long long *t = &h[(w * 16 + i) * 8];
+                                fprintf(f, "%zu %zu", w, i + 8);
+                                for (int k = 0; k < 8; ++k) fprintf(f, " %lld", t[k] ? t[k] - h[0] : -1ll);
+                                fprintf(f, "\n");
+                            }
+                        fclose(f);
+                    }
+                }
+                return 1;
+            }
+        }
+    }
     // per-warp staging (two buffers per worker warp): room for ~10 bits per sample, at most the
     // worst case; a wave that outgrows it is packed straight into its record in HBM.  Short
     // waves: 12 worker warps per CTA, two CTAs per SM; longer ones: 8 worker warps (larger staging).
@@ -1272,14 +1888,13 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
     if (stage > worst) stage = worst;
     if (stage < 64u) stage = 64u;
     stage = (stage + 3u) & ~3u;
-    auto launch = [&](auto kernel, bool &attr_set, int nworkers) {
+    auto launch = [&](auto kernel, DeviceOnce &attr_set, int nworkers) {
         const size_t smem = (size_t)stage * 2 * nworkers * sizeof(uint32_t);   // two buffers per worker warp
         const int nthreads = (nworkers + 1) * 32;
         const uint32_t ntiles = (p.nwaves + nworkers - 1) / nworkers;
-        if (!attr_set) {
+        if (attr_set.first()) {
             cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            attr_set = true;
         }
         int occ = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, nthreads, smem);
@@ -1288,7 +1903,7 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
         if (grid > ntiles) grid = ntiles;
         kernel<<<grid, nthreads, smem, st>>>(p, stage, ntiles);
     };
-    static bool attr12 = false, attr8 = false, attr8n = false;   // per K (this function is a template)
+    static DeviceOnce attr12, attr8, attr8n;                     // per K (this function is a template)
     if (!md.delta) launch(encode_tile_kernel<K, 2, false, 8>, attr8n, 8);    // no delta (filter [1] / pre-filtered input)
     else if (twelve) launch(encode_tile_kernel<K, 2, true, 12>, attr12, 12);
     else launch(encode_tile_kernel<K, 2, true, 8>, attr8, 8);

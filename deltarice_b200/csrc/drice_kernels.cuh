@@ -55,6 +55,11 @@ struct EncodeMode {
     uint32_t        lane_slot_words;
     uint32_t       *lane_state;         // [ntasks][6][32]: lane state parked between time slices
     uint32_t       *lane_slice_done;    // [ntasks], zeroed: slices a task has finished
+    // segment encoder: words of the largest record the previous batch of this context produced
+    // (0 = unknown: room for 10 bits per sample), and where this launch reports its own
+    uint32_t        seg_words_hint;
+    uint32_t        seg_lane_hint;      // same for the longest per-lane stream
+    uint32_t       *seg_max_words;
 };
 
 // generic pre-filter (src/deltaRice.c:64-74 / :91-102), taps by value
@@ -96,6 +101,78 @@ struct ParseParams {
     int             k;
     int             identity;           // 1: write the decoded values themselves (no inverse delta)
 };
+
+// ---- per-device launch state ------------------------------------------------------------------
+// cudaFuncSetAttribute (dynamic shared memory opt-in) and the SM count belong to a DEVICE, and one
+// process may hold contexts on several (drice_create(ctx, device)): everything cached about a
+// launch is keyed by the current device.
+constexpr int kMaxDevices = 64;
+inline int current_device()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+inline int device_sm_count()
+{
+    static int sms[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!sms[dev]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = n > 0 ? n : 148;
+    }
+    return sms[dev];
+}
+// one flag per device: `if (once.first()) cudaFuncSetAttribute(...)`; declare it `static` next to
+// the launch it guards (benign race: the attribute calls are idempotent)
+struct DeviceOnce {
+    unsigned long long done = 0;
+    bool first()
+    {
+        const unsigned long long bit = 1ull << current_device();
+        if (done & bit) return false;
+        done |= bit;
+        return true;
+    }
+};
+
+#ifdef __CUDACC__
+// ---- mbarrier + bulk async copy (TMA 1-D, SASS UBLKCP) ------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t mbar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
+{
+    while (!mbar_try_wait(mbar, parity)) {}
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes on `mbar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+#endif
 
 // launchers (drice_encode.cu / drice_decode.cu); return launches enqueued
 int launch_encode(const EncodeParams &p, const EncodeMode &m, uint32_t max_wave_len, cudaStream_t st);
