@@ -961,8 +961,6 @@ __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2) parse_wide_kernel(cons
     }
 }
 
-int g_dec_sms = 0;
-
 // warps per SM: as many as fit, trimmed so that the last round of warp tasks is nearly full
 int pick_parse_warps(uint32_t ngroups, int sms, int max_warps)
 {
@@ -979,14 +977,9 @@ int pick_parse_warps(uint32_t ngroups, int sms, int max_warps)
 
 int launch_parse_impl(const ParseParams &p, cudaStream_t st)
 {
-    if (!g_dec_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_dec_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_dec_sms <= 0) g_dec_sms = 148;
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
+    const int g_dec_sms = device_sm_count();
+    static DeviceOnce attr_set;                          // (function attributes belong to a device)
+    if (attr_set.first()) {
         cudaFuncSetAttribute(parse_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
         cudaFuncSetAttribute(parse_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         cudaFuncSetAttribute(parse_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
@@ -995,7 +988,6 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
         cudaFuncSetAttribute(parse_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         cudaFuncSetAttribute(parse_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
         cudaFuncSetAttribute(parse_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        attr_set = true;
     }
     // small batches: one CTA per wave (parallel inside the wave) instead of one lane per wave
     {
@@ -1005,15 +997,14 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
             wide = e ? atol(e) : (long)kWideMaxWaves;
         }
         if ((long)p.nwaves <= wide && p.max_n <= 8192u) {
-            static bool wattr = false;
+            static DeviceOnce wattr;
             const size_t wsmem = (size_t)(kWideMaxWords + 4 + (1 << kWideLutBits) + 2 * kWideThreads) * 4 +
                                  (size_t)kWideMaxRuns * 32 + kWideMaxRuns + 16;
-            if (!wattr) {
+            if (wattr.first()) {
                 cudaFuncSetAttribute(parse_wide_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
                 cudaFuncSetAttribute(parse_wide_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
                 cudaFuncSetAttribute(parse_wide_kernel<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
                 cudaFuncSetAttribute(parse_wide_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
-                wattr = true;
             }
             if (p.nwaves <= (uint32_t)g_dec_sms) {           // fewer waves than SMs: the biggest CTA per wave
                 if (p.identity) parse_wide_kernel<true, 1024><<<p.nwaves, 1024, wsmem, st>>>(p);
@@ -1074,12 +1065,9 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
 int launch_locate(const LocateParams &p, cudaStream_t st)
 {
     if (p.nchunks == 0) return 0;
-    static bool attr_set = false;
+    static DeviceOnce attr_set;
     const size_t smem = (size_t)(kLocStages * kLocTileWords) * sizeof(uint32_t);
-    if (!attr_set) {
-        cudaFuncSetAttribute(locate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    if (attr_set.first()) cudaFuncSetAttribute(locate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     locate_kernel<<<p.nchunks, kLocThreads, smem, st>>>(p);
     return 1;
 }
