@@ -66,9 +66,8 @@ struct drice_ctx {
     int filter_len = 2;
     int filter[drice::kMaxFilter] = {1, -1};
     DevBuf d_filt;                       // generic filter: pre-filtered samples of the batch
-    DevBuf d_lane;                       // lane-per-wave encoder: one worst-case slot per wave
     DevBuf d_scan;                       // locate by scanning: per-tile header candidates
-    // segment encoder: the largest record (words) of recent batches sizes the per-wave staging of the
+    // the largest record (words) of the previous batch sizes the encoder's per-wave staging of the
     // next one.  The kernel raises d_hint[0]; the next call's prep kernel moves it to h_hint (mapped
     // pinned memory, read by the host without a synchronisation) and clears it.
     uint32_t *d_hint = nullptr;
@@ -199,7 +198,7 @@ __global__ void prep_kernel(uint32_t *dst, const uint32_t *src, uint32_t nwords,
     if (tid == 0 && status) *status = 0;
     if (tid == 0 && hint_dev) {                      // the previous batch's largest record -> host
         const uint32_t h = hint_dev[0];
-        if (h) { hint_host[0] = h; hint_host[1] = hint_dev[1]; hint_host[2] = hint_dev[2]; hint_dev[0] = 0; hint_dev[1] = 0; hint_dev[2] = 0; }
+        if (h) { hint_host[0] = h; hint_dev[0] = 0; }
     }
 }
 
@@ -424,7 +423,7 @@ extern "C" void drice_destroy(drice_ctx *ctx)
     }
     for (auto &t : ctx->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
-    ctx->d_tab.release(); ctx->d_scratch.release(); ctx->d_offs.release(); ctx->d_filt.release(); ctx->d_lane.release(); ctx->d_scan.release();
+    ctx->d_tab.release(); ctx->d_scratch.release(); ctx->d_offs.release(); ctx->d_filt.release(); ctx->d_scan.release();
     for (int i = 0; i < 2; ++i) {
         if (ctx->h_piece[i]) cudaFreeHost(ctx->h_piece[i]);
         if (ctx->ev_piece[i]) cudaEventDestroy(ctx->ev_piece[i]);
@@ -493,8 +492,7 @@ extern "C" int drice_timing_read(drice_ctx *ctx, double *ms, uint64_t *launches,
 
 extern "C" const char *drice_kernel_name(int kind)
 {
-    // kind 0 = the encode kernel of the batch: encode_lane_kernel (>= DRICE_ENC_LANE_MIN waves), else
-    // encode_tile_kernel / encode_multi_kernel
+    // kind 0 = the encode kernel of the batch: encode_tile_kernel / encode_multi_kernel
     static const char *names[DRICE_NUM_KERNELS] = {"encode_kernel", "locate_kernel", "parse_kernel"};
     return (kind >= 0 && kind < DRICE_NUM_KERNELS) ? names[kind] : nullptr;
 }
@@ -532,14 +530,10 @@ extern "C" int drice_encode_batch_dev_async(drice_ctx *ctx, const int16_t *d_raw
         return DRICE_OK;
     }
     if (!d_raw && off[nchunks] > 0) return fail(ctx, DRICE_E_PARAM, "null input");
-    // scratch: [ticket u32][pad] | look-back status u64 per tile (at most one per wave) | slices done
-    // u32 per lane-kernel task: all zeroed; then the parked lane states (not zeroed)
-    const size_t ntasks = ((size_t)g.nwaves + 31) / 32;
-    const size_t zeroed = ((size_t)g.nwaves * 8 + 16 + ntasks * 4 + 16 + 15) & ~(size_t)15;
-    const size_t state_off = (zeroed + 255) & ~(size_t)255;
-    const size_t scratch = state_off + ntasks * 6 * 32 * 4;
-    if (scratch > ctx->d_scratch.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
-    DR_CUDA(ctx, ctx->d_scratch.reserve(scratch));
+    // scratch: [ticket u32][pad] | look-back status u64 per tile (at most one per wave): all zeroed
+    const size_t zeroed = ((size_t)g.nwaves * 8 + 16 + 15) & ~(size_t)15;
+    if (zeroed > ctx->d_scratch.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
+    DR_CUDA(ctx, ctx->d_scratch.reserve(zeroed));
     uint64_t *d_soff, *d_unused;
     uint32_t *d_woff;
     rc = upload_tables(ctx, off, nullptr, g.wave_off.data(), nchunks, st, &d_soff, &d_unused, &d_woff,
@@ -567,18 +561,12 @@ extern "C" int drice_encode_batch_dev_async(drice_ctx *ctx, const int16_t *d_raw
     p.raw = src;
     EncodeMode md{};
     md.delta = ctx->filter_mode == 0;
-    // the hint is the largest record in WORDS of a recent batch; it only transfers to waves of the same length
-    if (ctx->hint_wave != g.max_wave || ctx->hint_k != k) ctx->h_hint[0] = ctx->h_hint[1] = 0;
-    md.seg_words_hint = ctx->h_hint[0];
-    md.seg_lane_hint = ctx->h_hint[1];
+    // the hint is the largest record in WORDS of the previous batch; it only transfers to waves of the same shape
+    if (ctx->hint_wave != g.max_wave || ctx->hint_k != k) ctx->h_hint[0] = 0;
+    md.words_hint = ctx->h_hint[0];
     ctx->hint_wave = g.max_wave;
     ctx->hint_k = k;
-    md.seg_max_words = ctx->d_hint;
-    {
-        static const bool debug = getenv("DRICE_DEBUG") != nullptr;
-        if (debug) fprintf(stderr, "[drice] previous batch: largest record %u words, longest lane stream %u words, %u waves packed in place\n",
-                           ctx->h_hint[0], ctx->h_hint[1], ctx->h_hint[2]);
-    }
+    md.max_words = ctx->d_hint;
     p.raw_samples = off[nchunks];
     p.out = d_out;
     p.out_cap_words = out_cap_bytes / 4;
@@ -593,27 +581,6 @@ extern "C" int drice_encode_batch_dev_async(drice_ctx *ctx, const int16_t *d_raw
     p.uniform_wpc = g.uniform_wpc;
     p.L = g.Lk;
     p.k = k;
-    // encode_lane_kernel (one LANE per wave) is opt-in: DRICE_ENC_LANE_MIN=<waves> sends batches of at
-    // least that many waves to it.  Measured on C2 it is 6 % faster than the warp-per-wave tile kernel
-    // (0.69 vs 0.735 ms: 19 instead of 31 instructions per sample) but it needs a worst-case slot per
-    // wave in HBM (1.7 GB per GB of samples) and moves 2.13 GB instead of 1.34 GB.
-    {
-        static long lane_min = -1;
-        if (lane_min < 0) {
-            const char *e = getenv("DRICE_ENC_LANE_MIN");
-            lane_min = e ? atol(e) : 0x7fffffffffffffffl;
-        }
-        const uint64_t slot = ((25ull * g.max_wave + 31ull) / 32ull + 7ull) & ~7ull;
-        const uint64_t bytes = slot * 4ull * g.nwaves;
-        if ((long)g.nwaves >= lane_min && g.max_wave > 0 && slot < (1ull << 31) && bytes <= (24ull << 30)) {
-            if (bytes > ctx->d_lane.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
-            DR_CUDA(ctx, ctx->d_lane.reserve((size_t)bytes));
-            md.lane_scratch = (uint32_t *)ctx->d_lane.p;
-            md.lane_slot_words = (uint32_t)slot;
-            md.lane_slice_done = (uint32_t *)((char *)ctx->d_scratch.p + 16 + (size_t)g.nwaves * 8);
-            md.lane_state = (uint32_t *)((char *)ctx->d_scratch.p + state_off);
-        }
-    }
     int nl;
     {
         TimedScope ts(ctx, DRICE_KERNEL_ENCODE, st);

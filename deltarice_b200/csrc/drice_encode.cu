@@ -6,31 +6,36 @@
 //   perWaveCompression                 src/deltaRice.c:365-381
 //   writeWholeCompressedByteString     src/deltaRice.c:383-436 (framing + compaction)
 //
-// The codec is integer-ALU bound on B200 long before it is HBM bound (the first version of
-// this file issued ~61 instructions per sample and ran at 15 % of the HBM roofline), so the
-// design goal of the tile kernel below is instructions per sample, not bytes:
+// The codec is issue / integer-pipe bound on B200 long before it is HBM bound (sm_100 takes one warp
+// instruction per two cycles on the ALU pipe and on the FMA pipe each), so the kernels are designed
+// around instructions per sample, not bytes.
 //
-//   * one CTA per wave ("waveform" of L <= 8192 samples), persistent CTAs taking waves from
-//     an atomic ticket, single pass over HBM;
-//   * a thread owns 16 consecutive samples = 8 packed int16x2 words.  Delta, zig-zag and the
-//     Rice split run on the packed words (PRMT / VIADD.16x2 / LOP3), two samples per
-//     instruction where the ISA allows;
-//   * two samples are merged into one "pair" code (<= 30 bits when k <= 7) with a single
-//     IMAD: value_lo * 2^len_hi + value_hi.  Pairs that contain an escape (quotient >= 8,
-//     25-bit code) are rare and take a divergent slow path;
-//   * bit offsets: warp shuffle scan + one REDUX over the warp totals (one barrier);
-//   * packing appends pairs to a 64/96-bit window with IMAD.WIDE (acc*2^len + value: the
-//     multiply IS the shift, and it runs on the FMA pipe, off the saturated ALU pipe) and
-//     emits finished 32-bit words to shared memory.  Every thread starts its window with the
-//     trailing bits of its predecessor (one shuffle; computed with a 32-bit IMAD chain
-//     before offsets are known), so every word is written exactly once, complete — no
-//     shared-memory atomics, no fix-up pass;
-//   * cross-wave offsets by decoupled look-back over one 64-bit status word per wave; the
-//     record [nwords][words] is then copied out coalesced, the first wave of a chunk also
-//     writes the chunk header [total].
+// encode_tile_kernel (waves of <= 8192 samples), single pass over HBM:
+//   * persistent CTAs of NW worker warps + 1 control warp; a tile = NW consecutive waves taken from an
+//     atomic ticket; ONE WARP ENCODES ONE WAVE, 16 samples (8 packed int16x2 words) per lane and round;
+//     the next round's words are loaded between the round's front-end and its packing;
+//   * table front-end (RiceParameter 2, 4, 8; encode_round_lut): t = delta + 4M on packed halves
+//     (PRMT / LOP3 / 2 x VIADD.16x2), the two (k+3)-bit fields become the offset of the pair's entry
+//     with LOP3 / IMAD / SHF, one LDS returns the pair's code | length << 24 from a skewed table in
+//     shared memory; pairs that hold an escape (a half outside the table) are redone per sample in a
+//     rare divergent path and their second code is appended after a per-position warp vote;
+//   * arithmetic front-end (every other parameter, pre-filtered input; encode_round): zig-zag on packed
+//     halves, two samples merged into one pair code with a single IMAD;
+//   * bit offsets: warp shuffle scan per round (the shuffle's own predicate guards the add), running
+//     base across rounds;
+//   * packing appends a code to a 64-bit window with IMAD.WIDE (acc * 2^len + value: the multiply IS
+//     the shift, and it runs on the FMA pipe) and emits finished 32-bit words to the warp's staging in
+//     shared memory; neighbouring lanes are stitched with one shuffle per round (the bits a lane leaves
+//     pending are OR-ed into the first word of the next lane): no shared-memory atomics;
+//   * cross-wave compaction without a second pass: the worker that finishes the tile's last wave
+//     publishes the tile's aggregate; the control warp resolves the tile's offset by decoupled look-back
+//     while the workers encode the next tile into their second staging buffer; the record
+//     [nwords][words] is copied out coalesced one iteration later, the first wave of a chunk also
+//     writes the chunk header [total].  A wave larger than its staging is packed a second time straight
+//     into its record.
 //
-// Waves longer than one tile (L > 8192) use encode_multi_kernel: a sizing sweep, then a
-// packing sweep that re-reads the wave and streams completed words straight to HBM.
+// Waves longer than one tile (L > 8192) use encode_multi_kernel: a sizing sweep, then a packing sweep
+// that re-reads the wave and streams completed words straight to HBM.
 #include "drice_kernels.cuh"
 
 #include <cstdio>
@@ -484,6 +489,286 @@ __device__ __forceinline__ uint32_t encode_wave(const int16_t *wave, uint32_t n,
     return st.base;
 }
 
+// ======================================================================================
+// table front-end: one shared-memory lookup per PAIR of samples
+// ======================================================================================
+// For 1 <= K <= 3 the Rice split of a pair of deltas (src/deltaRice.c:207-222) is a table: when both
+// deltas lie in [-R, R) with R = 4M (quotients < 8, no escape), the pair's code and length are a
+// function of 2(K+3) bits.  The lane forms t = delta + R on packed halves (no zig-zag: the table
+// absorbs it), one LOP3 / IMAD / SHF turn the two (K+3)-bit fields into the entry's offset and one
+// LDS fetches code | length << 24.  Halves outside [0, 2R) flag the pair: it is redone per sample
+// (escape rule, :223-228) in a rare divergent path, as in the arithmetic front-end.
+// Entry (lo, hi) sits at word lo + hi * (2^(K+3) + kSkew): deltas cluster around 0, so without the
+// skew the bank (= lo mod 32) would be the same handful for every lane.
+template <int K>
+struct LutConst {
+    static constexpr bool     kOk   = (K >= 1 && K <= 3);
+    static constexpr uint32_t R     = 4u << K;
+    static constexpr uint32_t IDXB  = K + 3;                                   // bits of one biased delta
+    static constexpr uint32_t kSkew = 5;
+    static constexpr uint32_t ROW   = (1u << IDXB) + kSkew;
+    static constexpr uint32_t LOW   = (2u * R - 1u) * 0x10001u;
+    static constexpr uint32_t HIGH  = ~LOW;
+    static constexpr uint32_t MULT  = 0x10000u + ROW;                          // (t & LOW) * MULT: the entry's index at bit 16
+    static constexpr uint32_t ENTRIES = (2u * R - 1u) * ROW + 2u * R;
+};
+template <int K>
+__device__ __forceinline__ void build_pair_table(uint32_t *tab, int tid, int nthreads)
+{
+    using C = LutConst<K>;
+    for (uint32_t i = tid; i < 4u * C::R * C::R; i += nthreads) {
+        const uint32_t tl = i & (2u * C::R - 1u), th = i >> C::IDXB;
+        const int dl = (int)tl - (int)C::R, dh = (int)th - (int)C::R;
+        const uint32_t ul = dl >= 0 ? 2u * dl : (uint32_t)(-2 * dl - 1), uh = dh >= 0 ? 2u * dh : (uint32_t)(-2 * dh - 1);
+        uint32_t vl, ll, vh, lh;
+        rice_code<K>(ul, vl, ll);
+        rice_code<K>(uh, vh, lh);
+        tab[tl + th * C::ROW] = ((vl << lh) | vh) | ((ll + lh) << 24);   // the first sample (low half) leads
+    }
+}
+__device__ __forceinline__ uint32_t lds32a(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// one step of a warp inclusive scan: the shuffle's own predicate (source lane in range) guards the add
+__device__ __forceinline__ uint32_t scan_up(uint32_t v, int d)
+{
+    uint32_t r;
+    asm volatile("{ .reg .u32 r0; .reg .pred p; shfl.sync.up.b32 r0|p, %1, %2, 0, 0xffffffff; @p add.u32 r0, r0, %1; mov.u32 %0, r0; }"
+                 : "=r"(r) : "r"(v), "r"(d));
+    return r;
+}
+
+// NW8 packed words (2 * NW8 consecutive samples) of one lane; same alignment rules as load_slot
+template <int NW8>
+__device__ __forceinline__ void load_words(uint32_t (&w)[NW8], const int16_t *q, uint32_t mis)
+{
+    if (mis == 0) {
+#pragma unroll
+        for (int v = 0; v < NW8 / 4; ++v) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(q) + v);
+            w[4 * v] = a.x; w[4 * v + 1] = a.y; w[4 * v + 2] = a.z; w[4 * v + 3] = a.w;
+        }
+    } else if (mis == 4) {
+#pragma unroll
+        for (int v = 0; v < NW8 / 2; ++v) {
+            const uint2 a = __ldg(reinterpret_cast<const uint2 *>(q) + v);
+            w[2 * v] = a.x; w[2 * v + 1] = a.y;
+        }
+    } else if ((mis & 1) == 0) {
+#pragma unroll
+        for (int v = 0; v < NW8; ++v) w[v] = __ldg(reinterpret_cast<const uint32_t *>(q) + v);
+    } else {
+        const uint32_t *qa = reinterpret_cast<const uint32_t *>(q - 1);
+        uint32_t t[NW8 + 1];
+        t[0] = (uint32_t)(uint16_t)q[0] << 16;
+#pragma unroll
+        for (int v = 1; v < NW8; ++v) t[v] = __ldg(qa + v);
+        t[NW8] = (uint32_t)(uint16_t)q[2 * NW8 - 1];
+#pragma unroll
+        for (int v = 0; v < NW8; ++v) w[v] = prmt(t[v], t[v + 1], 0x5432);
+    }
+}
+template <int NW8>
+__device__ __forceinline__ void load_words_tail(uint32_t (&w)[NW8], const int16_t *q, uint32_t mis, uint32_t nvalid,
+                                                const int16_t *hi)
+{
+#pragma unroll
+    for (int m = 0; m < NW8; ++m) w[m] = 0;
+    if (nvalid == 0) return;
+    if (q + 2 * NW8 <= hi) { load_words<NW8>(w, q, mis); return; }
+#pragma unroll
+    for (int i = 0; i < 2 * NW8; ++i)
+        if (q + i < hi) w[i >> 1] |= (uint32_t)(uint16_t)q[i] << (16 * (i & 1));
+}
+
+// t = delta + R on packed halves: w - sh = w + ~sh + 1 with sh = (low half of w << 16) | high half of prev
+template <int K, bool kDelta>
+__device__ __forceinline__ uint32_t biased_delta(uint32_t w, uint32_t prev)
+{
+    using C = LutConst<K>;
+    if (!kDelta) return __vadd2(w, C::R * 0x10001u);
+    return __vadd2(__vadd2(w, prmt(~prev, ~w, 0x5432)), (C::R + 1u) * 0x10001u);
+}
+
+// One round of the table front-end: 2 * NW8 samples per lane.  `prefetch` is called between the
+// front-end (which consumes w) and the scan / pack phase: the caller loads the NEXT round's words
+// into w there, so the loads fly while this round is packed and no register copies are needed.
+template <int K, int NW8, bool kDirect, bool kFull, bool kDelta, class Prefetch>
+__device__ __forceinline__ void encode_round_lut(uint32_t (&w)[NW8], uint32_t nvalid, bool last_lane, int lane,
+                                                 uint32_t *dst, uint32_t cap, SweepState &st, uint32_t tab,
+                                                 Prefetch &&prefetch)
+{
+    using C = LutConst<K>;
+    constexpr uint32_t SS = 2u * NW8;
+    if (!kFull && nvalid > 0 && nvalid < SS) {           // short last slot: see encode_round
+        const uint32_t sel_hi = kDelta ? 0x1010u : 0x4410u, sel_all = kDelta ? 0x3232u : 0x4444u;
+#pragma unroll
+        for (int v = 0; v < NW8; ++v) {
+            if (2u * v + 1 == nvalid) w[v] = prmt(w[v], 0, sel_hi);
+            if (v > 0 && 2u * v >= nvalid) w[v] = prmt(w[v - 1], 0, sel_all);
+        }
+    }
+    uint32_t pw = __shfl_up_sync(0xffffffffu, w[NW8 - 1], 1);
+    if (lane == 0) pw = st.prev_last;
+    st.prev_last = __shfl_sync(0xffffffffu, w[NW8 - 1], 31);
+
+    // ---- one lookup per pair ------------------------------------------------------------------
+    uint32_t ev[NW8], t[NW8];
+    uint32_t uor = 0;
+    {
+        uint32_t np = ~pw;
+#pragma unroll
+        for (int m = 0; m < NW8; ++m) {
+            if (kDelta) {
+                const uint32_t nw = ~w[m];
+                t[m] = __vadd2(__vadd2(w[m], prmt(np, nw, 0x5432)), (C::R + 1u) * 0x10001u);
+                np = nw;
+            } else {
+                t[m] = __vadd2(w[m], C::R * 0x10001u);
+            }
+            uor |= t[m];
+            ev[m] = lds32a(tab + (((t[m] & C::LOW) * C::MULT) >> 14));   // (the product's bits 14, 15 are zero)
+        }
+    }
+    // lengths sit in byte 3 and the codes stay below 2^20: eight entries add up without a carry into it
+    uint32_t T = 0;
+#pragma unroll
+    for (int h = 0; h < NW8 / 8; ++h) {
+        uint32_t sacc = 0;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) sacc += ev[8 * h + m];
+        T += sacc >> 24;
+    }
+    // A pair with a half outside the table is coded per sample (escape rule): its first sample's code
+    // replaces the entry, the second one's goes to sec[m] (0 = nothing: a zero-length append is a no-op),
+    // both as value | length << 24 (an escape's value has 17 bits)
+    const bool flagged = (uor & C::HIGH) != 0u;
+    const bool any_flag = __any_sync(0xffffffffu, flagged);
+    if (any_flag) {
+#pragma unroll
+        for (int m = 0; m < NW8; ++m) {
+            const uint32_t tt = t[m];
+            t[m] = 0;                                    // from here on t[m] is sec[m]
+            if (tt & C::HIGH) {
+                // zig-zag of the two deltas (t - R), then the escape-aware code of each
+                const uint32_t d2 = __vsub2(tt, C::R * 0x10001u);
+                const uint32_t U = __vadd2(d2, d2) ^ prmt(d2, 0, 0xbb99);
+                uint32_t v0, l0, v1, l1;
+                rice_code<K>(U & 0xFFFFu, v0, l0);
+                rice_code<K>(U >> 16, v1, l1);
+                T += l0 + l1 - (ev[m] >> 24);
+                ev[m] = v0 | (l0 << 24);
+                t[m] = v1 | (l1 << 24);
+            }
+        }
+    }
+    if (!kFull && nvalid < SS) T = nvalid ? T - (SS - nvalid) * (K + 1) : 0u;
+    prefetch();
+
+    // ---- warp exclusive scan of T ----------------------------------------------------------
+    uint32_t inc = T;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) inc = scan_up(inc, d);
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    const uint32_t b0 = st.base + inc - T;
+    st.base += total;
+    if (!kDirect && st.base > cap * 32u - 544u) st.ovf = true;     // (the round after this one may not fit)
+    if (st.ovf) return;
+
+    // ---- pack ----------------------------------------------------------------------------------
+    Packer<kDirect> pk;
+    pk.n = b0 & 31u;
+    uint32_t *const first = dst + (b0 >> 5);
+    pk.ptr = first;
+    pk.end = dst + cap;
+    pk.lo = 0;
+    const bool packs = kFull || nvalid > 0;
+    if (packs) {
+        if (!any_flag) {
+#pragma unroll
+            for (int m = 0; m < NW8; ++m) pk.put(ev[m] & 0xFFFFFFu, ev[m] >> 24);
+        } else {
+            const uint32_t amask = kFull ? 0xffffffffu : __activemask();
+#pragma unroll
+            for (int m = 0; m < NW8; ++m) {
+                pk.put(ev[m] & 0xFFFFFFu, ev[m] >> 24);
+                if (__any_sync(amask, t[m] != 0u)) pk.put(t[m] & 0xFFFFFFu, t[m] >> 24);
+            }
+        }
+    }
+    // ---- stitch the lanes (see encode_round) ---------------------------------------------------
+    uint32_t frag;
+    asm("shl.b32 %0, %1, %2;" : "=r"(frag) : "r"(pk.lo), "r"(32u - pk.n));
+    if (!packs) frag = 0;
+    uint32_t from_prev = __shfl_up_sync(0xffffffffu, frag, 1);
+    if (lane == 0) from_prev = st.carry_round;
+    if (kFull && !kDirect) {
+        // a full lane holds >= 16 (K + 1) >= 32 bits: its first word is in the staging already
+        *first |= from_prev;
+    } else if (packs) {
+        const bool flushed = pk.ptr != first;
+        if (flushed) { if (from_prev) { if (!kDirect || first < pk.end) *first |= from_prev; } }
+        else frag |= from_prev;
+    }
+    st.carry_round = __shfl_sync(0xffffffffu, frag, 31);
+    if (!kFull && last_lane && packs) {
+        if (pk.n) pk.store(pk.ptr, frag);
+        if (st.base & 31u) dst[st.base >> 5] &= 0xFFFFFFFFu << (32u - (st.base & 31u));
+    }
+}
+
+// Sweep over one wave with the table front-end: rounds of 32 * 2 * NW8 samples while they are full,
+// then at most 2 * NW8 / 16 generic rounds of 512 (the wave's last lane must close the final word in one).
+template <int K, int NW8, bool kDirect, bool kDelta>
+__device__ __forceinline__ uint32_t encode_wave_lut(const int16_t *wave, uint32_t n, const int16_t *raw_hi, int lane,
+                                                    uint32_t *dst, uint32_t cap, bool *overflow, uint32_t tab)
+{
+    constexpr uint32_t kBig = 64u * NW8;                 // samples per full round
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(wave) & 15u) >> 1);
+    const uint32_t nbig = n ? (n - 1u) / kBig : 0u;      // the rest (1 .. kBig samples) goes to the generic rounds
+    SweepState st;
+    st.base = 0;
+    st.carry_round = 0;
+    st.prev_last = 0;
+    st.ovf = false;
+    uint32_t done = nbig * kBig;
+    if (nbig) {
+        uint32_t w[NW8];
+        const int16_t *q = wave + lane * (2 * NW8);
+        load_words<NW8>(w, q, mis);
+        for (uint32_t r = 0; r < nbig; ++r) {
+            q += kBig;
+            encode_round_lut<K, NW8, kDirect, true, kDelta>(w, 2u * NW8, false, lane, dst, cap, st, tab, [&] {
+                if (r + 1 < nbig) load_words<NW8>(w, q, mis);
+            });
+        }
+    }
+    // generic rounds of 512 samples (16 per lane)
+    do {
+        const uint32_t s0 = done + lane * 16u;
+        const int32_t rem = (int32_t)n - (int32_t)s0;
+        const uint32_t nv = rem >= 16 ? 16u : (rem > 0 ? (uint32_t)rem : 0u);
+        uint32_t w8[8];
+        load_words_tail<8>(w8, wave + s0, mis, nv, raw_hi);
+        encode_round_lut<K, 8, kDirect, false, kDelta>(w8, nv, nv > 0 && s0 + 16u >= n, lane, dst, cap, st, tab, [] {});
+        done += 512u;
+    } while (done < n);
+    __syncwarp();
+    *overflow = st.ovf;
+    return st.base;
+}
+// the rare wave that outgrew its staging: out of line, so that it stays out of the hot code
+template <int K, int NW8, bool kDelta>
+__device__ __noinline__ void encode_wave_lut_in_place(const int16_t *wave, uint32_t n, const int16_t *raw_hi, int lane,
+                                                      uint32_t *dst, uint32_t cap, uint32_t tab)
+{
+    bool dummy;
+    encode_wave_lut<K, NW8, true, kDelta>(wave, n, raw_hi, lane, dst, cap, &dummy, tab);
+}
+
 // ---- tile kernel ----------------------------------------------------------------------------
 // A tile = NW consecutive waves, taken by one persistent CTA of NW worker warps +
 // one control warp.  Per iteration a worker encodes ONE wave of the current tile into one of its
@@ -501,9 +786,29 @@ constexpr int kRing = 3;
 // NW worker warps (+ 1 control warp) per CTA: 12 for short waves (two CTAs per SM: measured best,
 // 0.69 vs 0.74 ms for 3 x 8 on C2; 13 and 14 lose to register pressure), 8 when the staging of
 // longer waves needs the room
-template <int K, int MINB, bool kDelta, int NW>
+// LUT: 0 = arithmetic front-end (encode_round), 1 = table front-end (1 <= K <= 3), 16 samples per lane and round
+// (32 per lane were measured too: twice as slow - registers spill and the unrolled round outgrows the
+// instruction cache)
+template <int LUT> struct LutVariant { static constexpr int NW8 = 8; };
+template <int K, bool kDirect, bool kDelta, int LUT>
+__device__ __forceinline__ uint32_t encode_wave_any(const int16_t *wave, uint32_t n, const int16_t *raw_hi, int lane,
+                                                    uint32_t *dst, uint32_t cap, bool *overflow, uint32_t tab)
+{
+    if constexpr (LUT == 0) {
+        return encode_wave<K, kDirect, kDelta>(wave, n, raw_hi, lane, dst, cap, overflow);
+    } else if constexpr (kDirect) {
+        encode_wave_lut_in_place<K, LutVariant<LUT>::NW8, kDelta>(wave, n, raw_hi, lane, dst, cap, tab);
+        return 0;
+    } else {
+        return encode_wave_lut<K, LutVariant<LUT>::NW8, false, kDelta>(wave, n, raw_hi, lane, dst, cap, overflow, tab);
+    }
+}
+template <int K, int LUT>
+constexpr size_t lut_table_bytes() { return LUT == 0 ? 0 : (size_t)((LutConst<K>::ENTRIES + 3u) & ~3u) * 4; }
+
+template <int K, int MINB, bool kDelta, int NW, int LUT = 0>
 __global__ void __launch_bounds__((NW + 1) * 32, MINB)
-encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint32_t ntiles)
+encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint32_t ntiles, uint32_t *const max_words)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t s_tile[kRing];                   // tile index of the iteration
@@ -517,6 +822,12 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
 
     if (threadIdx.x < kRing) { s_flag[threadIdx.x] = 0; s_cnt[threadIdx.x] = 0; }
     if (threadIdx.x == 0) s_tile[0] = atomicAdd(p.ticket, 1u);
+    uint32_t tab = 0;                                    // shared address of the pair table (behind the staging)
+    if constexpr (LUT != 0) {
+        uint32_t *const tabp = smem + (size_t)(2 * NW) * stage_words;
+        build_pair_table<K>(tabp, threadIdx.x, (NW + 1) * 32);
+        tab = (uint32_t)__cvta_generic_to_shared(tabp);
+    }
     __syncthreads();
 
     if (control) {
@@ -547,6 +858,7 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
     uint32_t nwords_prev = 0;
     bool have_prev = false, ovf_prev = false;
     wg_prev.g = 0xffffffffu;
+    uint32_t largest = 0;                                // largest record of this warp (sizes the next batch's staging)
     for (uint32_t it = 0;; ++it) {
         const int par = it & 1, slot = it % kRing;
         const uint32_t tile = s_tile[slot];
@@ -562,9 +874,10 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
                 have = true;
                 wg = locate_wave(p, g);
                 if (wg.chunk_total) {
-                    nwords = (encode_wave<K, false, kDelta>(p.raw + wg.begin, wg.n, raw_hi, lane, stage0 + par * stage_words,
-                                                    stage_words, &ovf) + 31u) >> 5;
+                    nwords = (encode_wave_any<K, false, kDelta, LUT>(p.raw + wg.begin, wg.n, raw_hi, lane, stage0 + par * stage_words,
+                                                             stage_words, &ovf, tab) + 31u) >> 5;
                     mine = nwords + 1u;
+                    largest = nwords > largest ? nwords : largest;
                 }
                 mine += wg.first;                            // empty chunk: header only
             }
@@ -617,7 +930,7 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
                         for (uint32_t i = lane; i < nwords_prev; i += 32) rec[1 + i] = src[i];
                     } else {                                 // larger than the staging: pack in place
                         bool dummy;
-                        encode_wave<K, true, kDelta>(p.raw + wg_prev.begin, wg_prev.n, raw_hi, lane, rec + 1, nwords_prev, &dummy);
+                        encode_wave_any<K, true, kDelta, LUT>(p.raw + wg_prev.begin, wg_prev.n, raw_hi, lane, rec + 1, nwords_prev, &dummy, tab);
                     }
                 }
             }
@@ -632,6 +945,7 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
         // workers only (the control warp runs on its own clock)
         asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
     }
+    if (lane == 0 && max_words && largest) atomicMax(max_words, largest);
 }
 
 // zig-zag of the 16-bit wrapped difference cur-prev (src/deltaRice.c:57-62, :207-211)
@@ -640,874 +954,6 @@ __device__ __forceinline__ uint32_t zigzag_delta(int cur, int prev)
     const int t = cur - prev;
     const uint32_t s = (uint32_t)((int)((uint32_t)t << 16) >> 31);
     return (((uint32_t)t << 1) ^ s) & 0xFFFFu;
-}
-
-// ======================================================================================
-// lane kernel: one LANE per wave (large batches)
-// ======================================================================================
-// With hundreds of thousands of waves in a batch the parallelism is across waves, as in the
-// decoder: every lane encodes its OWN wave sequentially, so nothing is shared inside a wave -
-// no per-round warp scan, no stitching of neighbouring lanes' bits, no warp-uniform escape
-// handling: delta / zig-zag on packed halves, pair codes, and the multiply-append packer are the
-// whole loop (17 instead of 31 instructions per sample).  The price is that a wave's size is only
-// known when it is done, so the lane first packs into a worst-case sized SLOT of an HBM scratch
-// (32-byte sectors, through a 32-word ring in shared memory), and when the 32 waves of the warp
-// task are finished the warp resolves the task's offset by decoupled look-back over TASKS and
-// copies the records to their final place, coalesced (the slots are still in L2 for the most part).
-//   input:  one 32-byte sector per lane and 16 samples, requested a block ahead;
-//   output: ring[word][lane] (bank = lane), flushed as full sectors.
-constexpr int kLaneWarps = 17;               // per CTA; two CTAs per SM
-constexpr int kLaneRingWords = 32;           // per lane
-
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v)
-{
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t addr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-struct Sector { uint32_t w[8]; };
-__device__ __forceinline__ Sector ldg_sector(const void *p)
-{
-    Sector r;
-    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
-                 : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void stg_sector(void *p, const uint32_t (&v)[8])
-{
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
-                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
-}
-__device__ __forceinline__ uint32_t ldg_cg_u32(const uint32_t *p)
-{
-    uint32_t v;
-    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v)
-{
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint4 ldg_cg_v4(const uint32_t *p)
-{
-    uint4 v;
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
-
-// bit packer of one lane over its whole wave (same multiply-append as Packer); finished words go
-// to the lane's ring, full sectors of the ring to the wave's scratch slot
-struct LanePacker {
-    uint32_t lo, n;             // pending bits in the low n (< 32) bits of lo
-    uint32_t wcount;            // words produced so far
-    uint32_t flushed;           // words already in the slot (multiple of 8)
-    uint32_t ring_b;            // shared address of the lane's ring row 0
-    uint32_t *slot;
-
-    __device__ __forceinline__ void put(uint32_t v, uint32_t len)
-    {
-        const uint64_t a = mul_wide(lo, pow2(len));
-        const uint32_t alo = (uint32_t)a | v;
-        n += len;
-        if (n >= 32u) {
-            n -= 32u;
-            sts32(ring_b + ((wcount & (kLaneRingWords - 1u)) << 7), __funnelshift_r(alo, (uint32_t)(a >> 32), n));
-            ++wcount;
-        }
-        lo = alo;
-    }
-    __device__ __forceinline__ void flush_sectors()
-    {
-        while (wcount - flushed >= 8u) {
-            const uint32_t ad = ring_b + ((flushed & (kLaneRingWords - 1u)) << 7);
-            uint32_t v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = lds32(ad + 128u * i);
-            stg_sector(slot + flushed, v);
-            flushed += 8u;
-        }
-    }
-    // closes the wave: the last partial word is left aligned, zero padded (:237-241)
-    __device__ __forceinline__ uint32_t finish()
-    {
-        if (n) {
-            uint32_t last;
-            asm("shl.b32 %0, %1, %2;" : "=r"(last) : "r"(lo), "r"(32u - n));
-            sts32(ring_b + ((wcount & (kLaneRingWords - 1u)) << 7), last);
-            ++wcount;
-        }
-        flush_sectors();
-        for (uint32_t i = flushed; i < wcount; ++i) slot[i] = lds32(ring_b + ((i & (kLaneRingWords - 1u)) << 7));
-        return wcount;
-    }
-};
-
-// one sample through the generic code (prologue / epilogue of a wave, escapes)
-template <int K>
-__device__ __forceinline__ void lane_put_sample(LanePacker &pk, uint32_t u)
-{
-    uint32_t v, l;
-    rice_code<K>(u, v, l);
-    pk.put(v, l);
-}
-
-// Work is handed out in SLICES: an item = (task of 32 waves, slice of kLaneSliceBlocks * 16 samples),
-// tickets run slice-major (every task's slice 0, then every task's slice 1, ...), and a lane's state
-// (packer, previous sample, position; the < 8 words still in its ring go to the slot) is parked in
-// global memory between slices.  With one long task per warp the SM's warp scheduler favours its
-// older CTA: that CTA's tasks finished ~170 us before the other's and half of the machine then ran at
-// half its warps and half its IPC (measured with per-task timestamps).  Slices keep all tasks in lock
-// step, so every warp has work until the end, whatever the number of tasks per warp.
-constexpr uint32_t kLaneSliceBlocks = 32;     // 512 samples per slice
-constexpr int      kLaneStateWords  = 6;      // per lane: lo, n, wcount, flushed, previous sample, samples done
-
-template <int K>
-__global__ void __launch_bounds__(kLaneWarps * 32, 2)
-encode_lane_kernel(const EncodeParams p, uint32_t *const scratch, const uint32_t slot_words, const uint32_t ngroups,
-                   const uint32_t nslices, uint32_t *const state, uint32_t *const slice_done, const uint32_t mul_x,
-                   const uint32_t neg_prev)
-{   // (mul_x, neg_prev): pre-filter mode, delta = (0xFFFF0001, 0xFFFFFFFF), none = (1, 0)
-    using C = RiceConst<K>;
-    constexpr bool kPairs = C::kPairs;
-    constexpr uint32_t M = C::M;
-    extern __shared__ __align__(16) uint32_t smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t ring_b = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)warp * (kLaneRingWords * 128u) + (uint32_t)lane * 4u;
-    asm volatile("mov.u32 %0, %0;" : "+r"(ring_b));         // keep it in a register (not recomputed per word)
-    const int16_t *const raw_hi = p.raw + p.raw_samples;
-    const int dmask = (int)neg_prev;                        // -1: delta, 0: none
-    const uint32_t nitems = ngroups * nslices;
-
-    while (true) {
-        uint32_t item = 0;
-        if (lane == 0) item = atomicAdd(p.ticket, 1u);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= nitems) break;
-        const uint32_t slice = item / ngroups;
-        const uint32_t grp = item - slice * ngroups;
-        const bool last_slice = slice == nslices - 1;
-        const uint32_t g = grp * 32u + (uint32_t)lane;
-        const bool active = g < p.nwaves;
-        WaveGeom wg;
-        wg.begin = 0; wg.n = 0; wg.chunk = 0; wg.first = 0; wg.chunk_total = 0; wg.g = g; wg.pad_ = 0;
-        if (active) wg = locate_wave(p, g);
-        const uint32_t n = wg.chunk_total ? wg.n : 0u;
-
-        LanePacker pk;
-        pk.lo = 0; pk.n = 0; pk.wcount = 0; pk.flushed = 0;
-        pk.ring_b = ring_b;
-        pk.slot = scratch + (size_t)g * slot_words;
-        int prevs = 0;                                       // previous sample of the wave
-        uint32_t done = 0;                                   // samples of the wave already coded
-        uint32_t *const st = state + ((size_t)grp * kLaneStateWords) * 32u + (uint32_t)lane;
-        __syncwarp();
-        if (slice) {
-            // the task's previous slice (handed out ngroups tickets ago) must have parked its state
-            if (lane == 0) {
-                while (ld_acquire_u32(slice_done + grp) < slice) __nanosleep(100);
-            }
-            __syncwarp();
-            pk.lo = ldg_cg_u32(st);
-            pk.n = ldg_cg_u32(st + 32);
-            pk.wcount = ldg_cg_u32(st + 64);
-            pk.flushed = ldg_cg_u32(st + 96);
-            prevs = (int)ldg_cg_u32(st + 128);
-            done = ldg_cg_u32(st + 160);
-            if (n) for (uint32_t i = pk.flushed; i < pk.wcount; ++i) sts32(ring_b + ((i & (kLaneRingWords - 1u)) << 7), ldg_cg_u32(pk.slot + i));
-        }
-        const int16_t *q = p.raw + wg.begin + done;
-        uint32_t left = n - done;
-
-        // ---- prologue (slice 0): single samples up to the first 32-byte boundary of the input -----
-        if (slice == 0) {
-            uint32_t pro = (uint32_t)((32u - (uint32_t)(reinterpret_cast<uintptr_t>(q) & 31u)) & 31u) >> 1;
-            if (pro > left) pro = left;
-            left -= pro;
-            done += pro;
-            for (; pro; --pro) {
-                const int x = *q++;
-                lane_put_sample<K>(pk, zigzag_delta(x, prevs & dmask));
-                prevs = x;
-            }
-        }
-        // ---- blocks of 16 samples = one sector ----------------------------------------------------
-        uint32_t nblk = left >> 4;
-        if (nblk > kLaneSliceBlocks) nblk = kLaneSliceBlocks;
-        const uint32_t maxblk = __reduce_max_sync(0xffffffffu, nblk);
-        uint32_t pw = (uint32_t)prevs << 16;                 // previous sample in the HIGH half
-        Sector nxt;
-#pragma unroll
-        for (int m = 0; m < 8; ++m) nxt.w[m] = 0;
-        if (nblk) nxt = ldg_sector(q);
-        const uint32_t MMr = opaque(C::MM), NNr = opaque(C::NN);
-        for (uint32_t b = 0; b < maxblk; ++b) {
-            if (b < nblk) {
-                const Sector cur = nxt;
-                q += 16;
-                if (b + 1 < nblk) nxt = ldg_sector(q);
-#pragma unroll
-                for (int m = 0; m < 8; ++m) {
-                    // delta + zig-zag on packed halves (src/deltaRice.c:57-62, :207-211)
-                    const uint32_t prev = m ? cur.w[m - 1] : pw;
-                    const uint32_t X = cur.w[m] * mul_x;
-                    const uint32_t Y = mad_lo(prev >> 16, neg_prev, cur.w[m]);
-                    const uint32_t D = prmt(Y, X, 0x7610);
-                    const uint32_t Sg = prmt(D, 0, 0xbb99);
-                    const uint32_t u2 = __vadd2(D, D) ^ Sg;
-                    if (kPairs) {
-                        if ((u2 & C::HM) == 0u) {            // two samples as one code of <= 30 bits
-                            const uint32_t V2 = (u2 | MMr) & NNr;
-                            const uint32_t qhi = u2 >> (16 + K), qlo = (u2 >> K) & C::QM;
-                            pk.put(mad_lo(V2 & 0xFFFFu, (2u * M) << qhi, V2 >> 16), qlo + qhi + 2u * (K + 1));
-                        } else {                             // a quotient >= 8: escape code(s)
-                            lane_put_sample<K>(pk, u2 & 0xFFFFu);
-                            lane_put_sample<K>(pk, u2 >> 16);
-                        }
-                    } else {
-                        lane_put_sample<K>(pk, u2 & 0xFFFFu);
-                        lane_put_sample<K>(pk, u2 >> 16);
-                    }
-                }
-                pw = cur.w[7];
-                pk.flush_sectors();
-            }
-        }
-        if (nblk) prevs = (int)pw >> 16;
-        done += nblk * 16u;
-        left -= nblk * 16u;
-
-        if (!last_slice) {
-            // ---- park the lane: pending words to the slot, state to global memory -----------------
-            if (n) for (uint32_t i = pk.flushed; i < pk.wcount; ++i) pk.slot[i] = lds32(ring_b + ((i & (kLaneRingWords - 1u)) << 7));
-            st[0] = pk.lo;
-            st[32] = pk.n;
-            st[64] = pk.wcount;
-            st[96] = pk.flushed;
-            st[128] = (uint32_t)prevs;
-            st[160] = done;
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) st_release_u32(slice_done + grp, slice + 1u);
-            continue;
-        }
-        // ---- epilogue (last slice): the last < 16 samples ----------------------------------------------
-        for (; left; --left) {
-            const int x = (q < raw_hi) ? (int)*q : 0;
-            ++q;
-            lane_put_sample<K>(pk, zigzag_delta(x, prevs & dmask));
-            prevs = x;
-        }
-        const uint32_t nwords = n ? pk.finish() : 0u;
-        __syncwarp();
-
-        // ---- the task's 32 records -> their final place --------------------------------------------
-        // (the last slices are handed out in task order, so the look-back finds its prefix close by)
-        const uint32_t rec_words = (active && wg.chunk_total) ? nwords + 1u : 0u;
-        const uint32_t mine = rec_words + (active ? wg.first : 0u);     // empty chunk: header only
-        uint32_t incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        if (lane == 0) st_relaxed_u64(p.lookback + grp, kFlagAggregate | (uint64_t)total);
-        const uint64_t excl = lookback_excl<400>(p.lookback, grp, total, lane);
-        const uint64_t off = excl + incl - mine;
-        const bool fits = off + mine <= p.out_cap_words;
-        if (!fits && mine) atomicOr(p.status, kErrCapacity);
-        if (grp == ngroups - 1 && lane == 31) p.chunk_byte_off[p.nchunks] = (excl + total) * 4;
-        if (active && wg.first) p.chunk_byte_off[wg.chunk] = off * 4;
-        if (active && fits) {
-            if (wg.first) p.out[off] = wg.chunk_total;
-            if (rec_words) p.out[off + wg.first] = nwords;
-        }
-        const uint64_t dst0 = off + wg.first + 1u;
-        const uint32_t ncopy = (fits && rec_words) ? nwords : 0u;
-        // 16 bytes per lane and load, 512 words of a record per step; the loads of the next record
-        // are in flight while the current one is stored (the copy is latency bound otherwise)
-        auto load4 = [&](uint4 (&v)[4], int s, uint32_t ns, uint32_t i0) {
-            const uint32_t *src = scratch + (size_t)(grp * 32u + (uint32_t)s) * slot_words;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t idx = i0 + (uint32_t)u * 128u + (uint32_t)lane * 4u;
-                v[u] = idx < ns ? ldg_cg_v4(src + idx) : make_uint4(0, 0, 0, 0);   // (slots are padded to 8 words)
-            }
-        };
-        auto store4 = [&](const uint4 (&v)[4], uint64_t ds, uint32_t ns, uint32_t i0) {
-            uint32_t *dst = p.out + ds;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t idx = i0 + (uint32_t)u * 128u + (uint32_t)lane * 4u;
-                if (idx + 4u <= ns) {
-                    dst[idx] = v[u].x; dst[idx + 1] = v[u].y; dst[idx + 2] = v[u].z; dst[idx + 3] = v[u].w;
-                } else if (idx < ns) {
-                    dst[idx] = v[u].x;
-                    if (idx + 1 < ns) dst[idx + 1] = v[u].y;
-                    if (idx + 2 < ns) dst[idx + 2] = v[u].z;
-                }
-            }
-        };
-        uint4 cur4[4], nxt4[4];
-        uint32_t ns = __shfl_sync(0xffffffffu, ncopy, 0);
-        load4(cur4, 0, ns, 0);
-        for (int s2 = 0; s2 < 32; ++s2) {
-            const uint64_t ds = __shfl_sync(0xffffffffu, dst0, s2);
-            const uint32_t ns_next = s2 < 31 ? __shfl_sync(0xffffffffu, ncopy, (s2 + 1) & 31) : 0u;
-            if (s2 < 31) load4(nxt4, s2 + 1, ns_next, 0);
-            store4(cur4, ds, ns, 0);
-            for (uint32_t i0 = 512u; i0 < ns; i0 += 512u) {     // records of more than 512 words
-                load4(cur4, s2, ns, i0);
-                store4(cur4, ds, ns, i0);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) cur4[u] = nxt4[u];
-            ns = ns_next;
-        }
-        __syncwarp();
-    }
-}
-
-// ======================================================================================
-// segment kernel: one WARP per wave, one LANE per contiguous SEGMENT (the default encoder)
-// ======================================================================================
-// The codec is bound by the integer pipes, not by HBM: on sm_100 the ALU pipe (LOP3 / SHF / PRMT /
-// IADD3) and the FMA pipe (IMAD, VIADD.16x2) each take one warp instruction per two cycles per SM
-// sub-partition and IMAD.WIDE / IMAD.HI one per four (tools/ubench_pipes.cu), so the kernel is
-// designed around pipe cycles per sample and around keeping many warps resident:
-//   * a wave is cut into BLOCKS of 16 samples = one 32-byte sector, counted from the 32-byte aligned
-//     address below the wave; a PIECE (<= 32 x nbmax blocks, normally the whole wave) deals its
-//     blocks evenly to the lanes as contiguous segments (the first lanes get one block more).  A lane
-//     reads its segment sector by sector straight into registers (ld.global.nc.v8, two sectors
-//     ahead): no shared-memory staging of the input, full sectors only, and the only irregular
-//     blocks of a wave are its first (the samples in front of the wave are zeroed: they then code as
-//     K+1 known bits each, which are skipped) and its last (padded with repeats of the last sample:
-//     zero deltas, cut off again);
-//   * every lane Rice-codes its segment sequentially into a private bit stream in shared memory
-//     ([word][lane] rings: conflict free) - no per-round warp scan, no stitching inside the loop.
-//     Two samples become one pair code with IMAD.WIDE (the multiply is the shift), appended to a
-//     64-bit window with one more IMAD.WIDE; the word under construction is stored unconditionally
-//     (a complete word overwrites the partial one), so the loop has no branch;
-//   * after the piece ONE warp scan of the lanes' bit counts gives every segment its bit offset in
-//     the wave and each lane funnel-shifts its stream into the wave's staging (boundary words are
-//     stitched with one shuffle);
-//   * tiles of NW waves, the control warp's decoupled look-back and the deferred coalesced copy-out
-//     are those of the tile kernel, without its per-iteration barrier among the workers.
-// A wave that outgrows its staging (or a lane its ring) is packed straight into its record by
-// encode_wave<.., true>.
-constexpr int      kSegMaxWorkers = 10;       // worker warps per CTA (+ 1 control warp); two CTAs per SM
-constexpr uint32_t kSegMinL       = 1024;     // shorter waves: tile kernel (lanes would idle)
-constexpr uint32_t kSegMaxBlocks  = 8;        // blocks per lane and piece
-
-struct SegLaunch {
-    uint32_t nworkers;      // worker warps per CTA (+ 1 control warp)
-    uint32_t nbmax;         // blocks (of 16 samples) per lane and piece, <= kSegMaxBlocks
-    uint32_t lane_words;    // words of one lane's private stream ring: a power of two
-    uint32_t stage_words;   // words of a wave's merged stream (nstage buffers per worker)
-    uint32_t nstage;        // 2 or 3: a wave is copied out nstage - 1 iterations after it was encoded
-    uint32_t ntiles;
-    uint32_t *max_words;    // hints for the next call (may be null): [0] largest record, [1] largest lane stream (words)
-    // multiplier constants of the inner loop, passed as PARAMETERS: a power of two the compiler can
-    // see is strength-reduced to shifts, i.e. moved from the FMA pipe back to the busier ALU pipe
-    uint32_t mulx;          // 0xFFFF0001: w * mulx has hi(w) - lo(w) in its high half
-    uint32_t p16;           // 2^16
-    uint32_t p16mk;         // 2^(16-K)
-    uint32_t four;          // 4
-    uint32_t dbg;           // DRICE_ENC_SEG_DBG (timing experiments only; output is wrong when set)
-    long long *trace;       // DRICE_ENC_SEG_TRACE: clock64 stamps of CTA 0 (diagnostics), else null
-};
-
-__device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c)
-{
-    uint64_t d;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
-    return d;
-}
-// (a ^ b) & c and (a ^ b) & ~c in one LOP3 each; (a & b) | c
-__device__ __forceinline__ uint32_t xor_and(uint32_t a, uint32_t b, uint32_t c)
-{
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ uint32_t xor_andn(uint32_t a, uint32_t b, uint32_t c)
-{
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0x14;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c)
-{
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-
-struct SegPacker {
-    uint32_t acc;       // pending bits in the low (b & 31) bits, stale above
-    uint32_t b;         // bits produced so far in this piece
-    uint32_t base;      // shared address of the lane's ring word 0 (the ring block is aligned to its size)
-    uint32_t wmask;     // (lane_words - 1) << 7: byte offset of a ring word
-    // appends a code of `len` <= 30 bits given as two disjoint bit fields v0 | v1 (P = 2^len).  The
-    // word under construction is stored every time: if the code completes it the store is final,
-    // otherwise a later store overwrites it.  (The fields are joined with a three-input OR, not an
-    // add, so that they cannot be folded into the multiply as a 64-bit addend.)
-    __device__ __forceinline__ void append(uint32_t v0, uint32_t v1, uint32_t P, uint32_t len, const SegLaunch &c)
-    {
-        const uint64_t a = mad_wide(acc, P, 0ull);
-        const uint32_t alo = (uint32_t)a | v0 | v1;          // the low `len` bits of the product are 0
-        const uint32_t at = and_or(b * c.four, wmask, base); // word b >> 5 of the ring
-        b += len;
-        sts32(at, __funnelshift_r(alo, (uint32_t)(a >> 32), b));
-        acc = alo;
-    }
-};
-
-// two samples (both quotients < 8) as one code: VL = packed remainders, QK = packed quotient * M.
-template <int K>
-__device__ __forceinline__ void seg_put_pair(SegPacker &pk, uint32_t VL, uint32_t QK, const SegLaunch &c)
-{
-    const uint64_t qs = mad_wide(QK, c.p16mk, 0ull);                         // {q_hi, q_lo << 16}
-    const uint32_t q_hi = (uint32_t)(qs >> 32);
-    const uint32_t S = ((uint32_t)qs >> 16) + q_hi;                           // q_lo + q_hi (one LEA.HI)
-    const uint32_t Ph = __funnelshift_l(0u, (2u << K) << 16, q_hi);           // 2^(16 + len_hi)
-    // terminator bits: VIADD.16x2 (FMA pipe); the halves cannot carry (r < M)
-    const uint64_t sp = mad_wide(__vadd2(VL, RiceConst<K>::MM), c.p16, 0ull); // {r_hi + M, (r_lo + M) << 16}
-    const uint64_t t = mad_wide((uint32_t)sp, Ph, 0ull);                      // high word: (r_lo + M) * 2^len_hi
-    const uint32_t P = __funnelshift_l(0u, 1u << (2 * K + 2), S);
-    pk.append((uint32_t)(t >> 32), (uint32_t)(sp >> 32), P, S + (2u * K + 2u), c);
-}
-template <int K>
-__device__ __forceinline__ void seg_put_single(SegPacker &pk, uint32_t u, const SegLaunch &c)
-{
-    uint32_t v, l;
-    rice_code<K>(u, v, l);
-    pk.append(v, 0u, pow2(l), l, c);
-}
-
-// 8 samples = 4 packed words of one lane.  pw = the word before them (previous sample in its high half).
-template <int K, bool kDelta>
-__device__ __forceinline__ void seg_block(SegPacker &pk, const uint32_t (&w)[4], uint32_t &pw, const SegLaunch &c)
-{
-    using C = RiceConst<K>;
-    constexpr uint32_t LOW = ((1u << K) - 1u) * 0x10001u;
-    uint32_t VL[4], QK[4];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-        // delta + zig-zag on packed halves (src/deltaRice.c:57-62, :207-211)
-        uint32_t D = w[m];
-        if (kDelta) {
-            const uint32_t prev = m ? w[m - 1] : pw;
-            const uint32_t X = w[m] * c.mulx;                // high half: hi(w) - lo(w)
-            const uint32_t Y = w[m] - (prev >> 16);          // low half:  lo(w) - hi(prev)
-            D = prmt(Y, X, 0x7610);
-        }
-        const uint32_t D2 = __vadd2(D, D), Sg = prmt(D, 0, 0xbb99);    // U = D2 ^ Sg
-        VL[m] = xor_and(D2, Sg, LOW);
-        QK[m] = xor_andn(D2, Sg, LOW);
-    }
-    pw = w[3];
-    if constexpr (C::kPairs) {
-        const bool esc = (((QK[0] | QK[1]) | (QK[2] | QK[3])) & C::HM) != 0u;
-        if (!__any_sync(__activemask(), esc)) {
-#pragma unroll
-            for (int m = 0; m < 4; ++m) seg_put_pair<K>(pk, VL[m], QK[m], c);
-        } else {                                    // some lane holds a quotient >= 8 (escape code)
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                if (__any_sync(__activemask(), (QK[m] & C::HM) != 0u)) {
-                    const uint32_t U = VL[m] | QK[m];
-                    seg_put_single<K>(pk, U & 0xFFFFu, c);
-                    seg_put_single<K>(pk, U >> 16, c);
-                } else {
-                    seg_put_pair<K>(pk, VL[m], QK[m], c);
-                }
-            }
-        }
-    } else {
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const uint32_t U = VL[m] | QK[m];
-            seg_put_single<K>(pk, U & 0xFFFFu, c);
-            seg_put_single<K>(pk, U >> 16, c);
-        }
-    }
-}
-
-// block B (16 samples from origin + 32 B) of a wave.  Only the wave's first and last block can be ragged
-// (samples in front of the wave / behind it inside the 32-byte sector): those two sectors are patched
-// once per wave into a 64-byte scratch of the warp in shared memory (seg_patch) and read from there.
-__device__ __forceinline__ Sector lds_sector(uint32_t addr)
-{
-    Sector r;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "r"(addr));
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ Sector seg_load(const unsigned char *origin, uint32_t B, uint32_t NB, bool lead, bool tail, uint32_t scratch)
-{
-    if ((B == 0u && lead) || (B + 1u == NB && tail)) return lds_sector(scratch + (B == 0u && lead ? 0u : 32u));
-    return ldg_sector(origin + (size_t)B * 32u);
-}
-// lanes 0..15: the 16 samples of the wave's first sector, lanes 16..31: of its last sector.  Samples in front
-// of the wave become 0, samples behind it repeat the last one (`fill`); nothing outside the wave is read.
-__device__ __forceinline__ void seg_patch(const unsigned char *origin, uint32_t NB, uint32_t mis, uint32_t span, uint32_t fill,
-                                          uint32_t scratch, int lane)
-{
-    const uint32_t idx = (lane < 16 ? 0u : (NB - 1u) * 16u) + ((uint32_t)lane & 15u);
-    uint32_t v = idx < mis ? 0u : fill;
-    if (idx >= mis && idx < span) v = *reinterpret_cast<const uint16_t *>(origin + (size_t)idx * 2u);
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(scratch + (uint32_t)lane * 2u), "h"((uint16_t)v) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void *p)
-{
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
-// the rare wave that outgrew its staging: out of line, so that it stays out of the instruction cache
-template <int K, bool kDelta>
-__device__ __noinline__ void encode_wave_in_place(const int16_t *wave, uint32_t n, const int16_t *raw_hi, int lane, uint32_t *dst, uint32_t cap)
-{
-    bool dummy;
-    encode_wave<K, true, kDelta>(wave, n, raw_hi, lane, dst, cap, &dummy);
-}
-
-// Shared control state of a CTA lives in a ring of kSegRing slots (iteration % kSegRing).  There is no
-// barrier among the workers.  A wave is copied out D = nstage - 1 iterations after it was encoded (the
-// merged stream waits in one of the worker's nstage staging buffers), when the control warp has long
-// resolved its tile's offset: a worker needs the offset of tile it-D to finish iteration it, and the
-// control warp needs every worker's size of that tile, so no worker is ever more than D+1 iterations
-// ahead of another and six slots are never reused too early.
-// The worker that COMPLETES tile it (the last to report its wave's size) claims the tile of iteration
-// it+2: tiles complete in ticket order machine-wide (a tile is claimed two iterations of its CTA's
-// slowest worker before it completes), so a look-back finds its predecessors published, and every
-// worker knows its next wave one iteration early: it prefetches that wave into L2 while it encodes.
-constexpr int kSegRing = 6;
-
-struct SegDeferred {                       // what the copy-out of a wave needs, parked in shared memory
-    uint64_t begin;
-    uint32_t n, chunk, chunk_total, nwords, flags;   // flags: 1 first, 2 have, 4 overflow
-    uint32_t pad_;
-};
-
-template <int K, bool kDelta>
-__global__ void __launch_bounds__((kSegMaxWorkers + 1) * 32, 2)
-encode_seg_kernel(const EncodeParams p, const SegLaunch sl)
-{
-    extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ uint32_t s_tile[8];                        // tile of iteration it (ring of 8)
-    __shared__ volatile uint32_t s_tag[8];                // = it + 1 once s_tile[it & 7] is valid
-    __shared__ uint32_t s_mine[kSegRing][kSegMaxWorkers]; // words each wave contributes
-    __shared__ uint32_t s_cnt[kSegRing];
-    __shared__ uint32_t s_total[kSegRing];
-    __shared__ uint64_t s_off[kSegRing];
-    __shared__ volatile uint32_t s_flag[kSegRing];        // = it + 1 once s_off is valid
-    __shared__ SegDeferred s_def[kSegMaxWorkers][3];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int NW = (int)sl.nworkers;
-    const bool control = warp == NW;
-    const uint32_t ntiles = sl.ntiles;
-    const uint32_t D = sl.nstage - 1u;                    // iterations between encoding a wave and copying it out
-
-    if (threadIdx.x < kSegRing) { s_flag[threadIdx.x] = 0; s_cnt[threadIdx.x] = 0; }
-    if (threadIdx.x < 8) s_tag[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_tile[0] = atomicAdd(p.ticket, 1u);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        s_tile[1] = atomicAdd(p.ticket, 1u);              // (after the machine's first round of claims, roughly)
-        s_tag[0] = 1;
-        s_tag[1] = 2;
-    }
-    __syncthreads();
-
-    if (control) {
-        for (uint32_t it = 0;; ++it) {
-            const int slot = it % kSegRing;
-            // sleeps on a named barrier (one per ring slot) until the tile's last worker arrives
-            asm volatile("bar.sync %0, 64;" ::"r"(2 + slot) : "memory");
-            const uint32_t tile = s_tile[it & 7];
-            if (tile >= ntiles) break;
-            const uint64_t mine = s_total[slot];
-            const uint64_t excl = lookback_excl(p.lookback, tile, mine, lane);
-            if (lane == 0) {
-                s_off[slot] = excl;
-                __threadfence_block();
-                s_flag[slot] = it + 1;
-                if (excl + mine > p.out_cap_words) atomicOr(p.status, kErrCapacity);
-                if (tile == ntiles - 1) p.chunk_byte_off[p.nchunks] = (excl + mine) * 4;
-            }
-            __syncwarp();
-        }
-        return;
-    }
-
-    // ---- workers ---------------------------------------------------------------------------
-    const uint32_t stage_words = sl.stage_words;
-    const uint32_t ring_bytes = sl.lane_words * 128u;                          // one warp's 32 lane rings
-    const uint32_t dyn = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t rings0 = (dyn + ring_bytes - 1u) & ~(ring_bytes - 1u);      // ring blocks are aligned to their size
-    const uint32_t stage_s0 = rings0 + (uint32_t)NW * ring_bytes + (uint32_t)warp * (sl.nstage * stage_words * 4u + 64u);
-    const uint32_t scratch = stage_s0 + sl.nstage * stage_words * 4u;         // the wave's ragged first / last sector
-    const int16_t *const raw_hi = p.raw + p.raw_samples;
-    SegPacker pk;
-    pk.base = rings0 + (uint32_t)warp * ring_bytes + (uint32_t)lane * 4u;
-    pk.wmask = (sl.lane_words - 1u) << 7;
-    const uint32_t ring_bits = (sl.lane_words - 1u) * 32u;                     // a lane past this has overflowed
-
-    uint32_t maxw = 0, maxlane = 0, novf = 0;
-    uint32_t buf = 0;                                    // staging buffer of this iteration: it % nstage
-    for (uint32_t it = 0;; ++it) {
-        const int slot = it % kSegRing;
-        const bool tr = sl.trace && blockIdx.x == 0 && it >= 8u && it < 24u;
-        long long *const trp = sl.trace + ((size_t)warp * 16u + (it - 8u)) * 8u;
-#define SEG_STAMP(k) do { if (tr && lane == 0) trp[k] = clock64(); } while (0)
-        SEG_STAMP(0);
-        while (s_tag[it & 7] != it + 1) __nanosleep(20);     // (claimed when tile it-2 completed: long ago)
-        __threadfence_block();
-        const uint32_t tile = s_tile[it & 7];
-        const bool live = tile < ntiles;
-        SegDeferred df;
-        df.begin = 0; df.n = 0; df.chunk = 0; df.chunk_total = 0; df.nwords = 0; df.flags = 0; df.pad_ = 0;
-        if (live) {
-            const uint32_t g = tile * (uint32_t)NW + (uint32_t)warp;
-            uint32_t mine = 0;
-            if (g < p.nwaves) {
-                const WaveGeom wg = locate_wave(p, g);
-
-                df.begin = wg.begin; df.n = wg.n; df.chunk = wg.chunk; df.chunk_total = wg.chunk_total;
-                df.flags = 2u | wg.first;
-                bool ovf = false;
-                uint32_t nwords = 0;
-                if (wg.chunk_total) {
-                    const uintptr_t wa = reinterpret_cast<uintptr_t>(p.raw + wg.begin);
-                    const unsigned char *const origin = reinterpret_cast<const unsigned char *>(wa & ~(uintptr_t)31);
-                    const uint32_t mis = (uint32_t)(wa & 31u) >> 1;            // samples between origin and the wave
-                    const uint32_t span = mis + wg.n;
-                    const uint32_t NB = (span + 15u) >> 4;                     // blocks of the wave
-                    SEG_STAMP(1);
-                    const bool lead = mis != 0u, tail = (span & 15u) != 0u;
-                    if (lead || tail) {
-                        uint32_t fill = 0;
-                        if (kDelta && tail) fill = (uint32_t)(uint16_t)p.raw[wg.begin + wg.n - 1u];
-                        seg_patch(origin, NB, mis, span, fill, scratch, lane);
-                        __syncwarp();
-                    }
-                    const uint32_t stage_s = stage_s0 + buf * stage_words * 4u;
-                    uint32_t Bw = 0;                 // bits of the wave merged so far
-                    uint32_t carry = 0;              // the wave's last, still partial word (left aligned)
-                    for (uint32_t blk0 = 0; blk0 < NB; blk0 += 32u * sl.nbmax) {
-                        // ---- this lane's segment of the piece: blocks [start, start + mb) ------------------
-                        const uint32_t pnb = NB - blk0 < 32u * sl.nbmax ? NB - blk0 : 32u * sl.nbmax;
-                        const uint32_t q = pnb >> 5, r = pnb & 31u;
-                        const uint32_t mb = q + ((uint32_t)lane < r ? 1u : 0u);
-                        const uint32_t start = blk0 + q * (uint32_t)lane + ((uint32_t)lane < r ? (uint32_t)lane : r);
-                        const uint32_t nact = q ? 32u : r;                        // lanes that hold blocks
-                        pk.acc = 0;
-                        pk.b = 0;
-                        if (mb) {
-                            uint32_t pw = 0;
-                            if (kDelta && start) pw = (uint32_t)*reinterpret_cast<const uint16_t *>(origin + (size_t)start * 32u - 2u) << 16;
-                            Sector c0 = seg_load(origin, start, NB, lead, tail, scratch), c1 = c0, c2 = c0;
-                            if (mb > 1u) c1 = seg_load(origin, start + 1u, NB, lead, tail, scratch);
-                            if (mb > 2u) c2 = seg_load(origin, start + 2u, NB, lead, tail, scratch);
-                            if (tr && lane == 0) { trp[2] = clock64(); trp[7] = (long long)(c0.w[0] & 1u) + clock64(); }
-                            for (uint32_t bl = 0; bl < mb; ++bl) {
-                                Sector cur = c0;
-                                c0 = c1;
-                                c1 = c2;
-                                if (bl + 3u < mb) c2 = seg_load(origin, start + bl + 3u, NB, lead, tail, scratch);
-#pragma unroll 1
-                                for (int half = 0; half < 2; ++half) {           // (one copy of the code: it has to stay in the instruction cache)
-                                    const uint32_t w4[4] = {cur.w[0], cur.w[1], cur.w[2], cur.w[3]};
-                                    seg_block<K, kDelta>(pk, w4, pw, sl);
-                                    cur.w[0] = cur.w[4]; cur.w[1] = cur.w[5]; cur.w[2] = cur.w[6]; cur.w[3] = cur.w[7];
-                                }
-                            }
-                            if (pk.b & 31u) {
-                                uint32_t last;
-                                asm("shl.b32 %0, %1, %2;" : "=r"(last) : "r"(pk.acc), "r"(32u - (pk.b & 31u)));
-                                sts32(and_or(pk.b << 2, pk.wmask, pk.base), last);
-                            }
-                        }
-                        __syncwarp();
-                        SEG_STAMP(3);
-                        maxlane = pk.b > maxlane ? pk.b : maxlane;
-                        // ---- bit offsets of the segments in the wave ---------------------------------------
-                        const uint32_t skip = (start == 0u && mb) ? mis * (K + 1u) : 0u;    // the zeroed samples in front
-                        uint32_t nbits = 0;
-                        if (mb) {
-                            nbits = pk.b - skip;
-                            if (start + mb == NB) nbits -= (NB * 16u - span) * (K + 1u);  // the repeats behind the wave
-                        }
-                        uint32_t inc = nbits;
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) {
-                            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-                            if (lane >= d) inc += t;
-                        }
-                        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-                        const uint32_t dbit = Bw + inc - nbits;                  // first bit of this lane's segment
-                        // every segment but the last holds >= 32 bits (a word then has at most two contributors)
-                        // and no lane has run around its ring
-                        const bool shape_ok = __all_sync(0xffffffffu, pk.b <= ring_bits && (!mb || (uint32_t)lane + 1u >= nact || nbits >= 32u));
-                        if (!shape_ok || ((Bw + total + 31u) >> 5) + 1u > stage_words) ovf = true;
-                        if (!ovf && !(sl.dbg & 1u)) {
-                            // ---- merge: funnel-shift the lane's stream to its place ------------------------
-                            uint32_t out_frag = 0, head = 0, last = 0;
-                            const uint32_t ebit = dbit + nbits;
-                            const uint32_t j0 = dbit >> 5, j1 = (ebit - 1u) >> 5;
-                            const bool tail_partial = (ebit & 31u) != 0u;
-                            const bool single = j0 == j1;
-                            const int32_t t = (int32_t)skip - (int32_t)dbit;
-                            const uint32_t tr = (uint32_t)t & 31u;
-                            const int32_t m0 = (int32_t)j0 + (t >> 5);           // stream word under stage word j0
-                            uint32_t pa = pk.base + (uint32_t)(m0 + 1) * 128u;    // address of stream word m0 + 1
-                            uint32_t sa = stage_s + j0 * 4u;
-                            if (nbits) {
-                                const uint32_t tmask = tail_partial ? ~(0xFFFFFFFFu >> (ebit & 31u)) : 0xFFFFFFFFu;
-                                uint32_t cur = m0 >= 0 ? lds32(pa - 128u) : 0u;
-                                uint32_t nx = lds32(pa);
-                                head = __funnelshift_l(nx, cur, tr) & (0xFFFFFFFFu >> (dbit & 31u));
-                                if (single) head &= tmask;
-                                uint32_t left = j1 - j0;                          // words after the first
-                                while (left > 4u) {                               // four words per step
-                                    const uint32_t a1 = lds32(pa + 128u), a2 = lds32(pa + 256u), a3 = lds32(pa + 384u), a4 = lds32(pa + 512u);
-                                    sts32(sa + 4u, __funnelshift_l(a1, nx, tr));
-                                    sts32(sa + 8u, __funnelshift_l(a2, a1, tr));
-                                    sts32(sa + 12u, __funnelshift_l(a3, a2, tr));
-                                    sts32(sa + 16u, __funnelshift_l(a4, a3, tr));
-                                    nx = a4;
-                                    pa += 512u;
-                                    sa += 16u;
-                                    left -= 4u;
-                                }
-                                while (left) {
-                                    cur = nx;
-                                    pa += 128u;
-                                    sa += 4u;
-                                    nx = lds32(pa);
-                                    const uint32_t f = __funnelshift_l(nx, cur, tr);
-                                    if (--left) sts32(sa, f); else last = f & tmask;
-                                }
-                                if (tail_partial && !single) out_frag = last;
-                            }
-                            uint32_t in_frag = __shfl_up_sync(0xffffffffu, out_frag, 1);
-                            if (lane == 0) in_frag = carry;
-                            if (nbits) {
-                                const uint32_t w0 = head | in_frag;
-                                if (single) {
-                                    if (tail_partial) out_frag = w0; else sts32(stage_s + j0 * 4u, w0);
-                                } else {
-                                    sts32(stage_s + j0 * 4u, w0);
-                                    if (!tail_partial) sts32(stage_s + j1 * 4u, last);
-                                }
-                            }
-                            carry = __shfl_sync(0xffffffffu, out_frag, (int)nact - 1);
-                        }
-                        Bw += total;
-                        __syncwarp();
-                    }
-                    SEG_STAMP(4);
-                    if (!ovf && (Bw & 31u) && lane == 0) sts32(stage_s + (Bw >> 5) * 4u, carry);
-                    nwords = (Bw + 31u) >> 5;
-                    mine = nwords + 1u;
-                    maxw = nwords > maxw ? nwords : maxw;
-                    __syncwarp();
-                }
-                df.nwords = nwords;
-                if (ovf) { df.flags |= 4u; ++novf; }
-                mine += wg.first;                            // empty chunk: header only
-            }
-            bool last = false;
-            if (lane == 0) {
-                s_mine[slot][warp] = mine;
-                __threadfence_block();
-                if (atomicAdd(&s_cnt[slot], 1u) == (uint32_t)NW - 1u) {
-                    // last worker of the tile: publish the tile's aggregate, claim the tile of iteration it + 2
-                    __threadfence_block();
-                    uint32_t total = 0;
-                    for (int w = 0; w < NW; ++w) total += s_mine[slot][w];
-                    st_relaxed_u64(p.lookback + tile, kFlagAggregate | (uint64_t)total);
-                    s_total[slot] = total;
-                    s_cnt[slot] = 0;
-                    s_tile[(it + 2) & 7] = atomicAdd(p.ticket, 1u);
-                    __threadfence_block();
-                    s_tag[(it + 2) & 7] = it + 3;
-                    last = true;
-                }
-            }
-            if (__shfl_sync(0xffffffffu, last, 0))           // wakes the control warp
-                asm volatile("bar.arrive %0, 64;" ::"r"(2 + slot) : "memory");
-        } else if (warp == 0) {
-            __threadfence_block();
-            asm volatile("bar.arrive %0, 64;" ::"r"(2 + slot) : "memory");   // lets the control warp see the end
-        }
-        if (lane == 0) s_def[warp][buf] = df;
-        __syncwarp();
-        SEG_STAMP(5);
-        // ---- copy out the wave(s) encoded D iterations ago (all that are left once the tiles have run out) ----
-        for (uint32_t back = D; back >= (live ? D : 1u); --back) {
-            if (it < back) continue;
-            const uint32_t jt = it - back;                       // iteration whose wave goes out
-            const uint32_t jb = jt % sl.nstage;
-            const SegDeferred d = s_def[warp][jb];
-            if (!(d.flags & 2u)) continue;
-            const int psl = jt % kSegRing;
-            while (s_flag[psl] != jt + 1) __nanosleep(400);      // tile offset: normally there long ago
-            __threadfence_block();
-            const uint32_t v = lane < NW ? s_mine[psl][lane] : 0u;
-            const uint32_t loff = __reduce_add_sync(0xffffffffu, lane < warp ? v : 0u);
-            const uint64_t off = s_off[psl] + loff;
-            const uint32_t first = d.flags & 1u;
-            const uint32_t rec_words = d.chunk_total ? d.nwords + 1u : 0u;
-            const bool fits = off + rec_words + first <= p.out_cap_words;
-            if (lane == 0 && first) p.chunk_byte_off[d.chunk] = off * 4;
-            if (fits) {
-                uint32_t *rec = p.out + off + first;
-                if (lane == 0) {
-                    if (first) p.out[off] = d.chunk_total;
-                    if (rec_words) rec[0] = d.nwords;
-                }
-                if (rec_words) {
-                    if (sl.dbg & 2u) {
-                    } else if (!(d.flags & 4u)) {
-                        uint32_t sa = stage_s0 + jb * stage_words * 4u + (uint32_t)lane * 4u;
-                        uint32_t *dst = rec + 1 + lane;
-                        uint32_t i = lane;
-                        for (; i + 96u < d.nwords; i += 128u, sa += 512u, dst += 128) {
-                            const uint32_t a0 = lds32(sa), a1 = lds32(sa + 128u), a2 = lds32(sa + 256u), a3 = lds32(sa + 384u);
-                            dst[0] = a0; dst[32] = a1; dst[64] = a2; dst[96] = a3;
-                        }
-                        for (; i < d.nwords; i += 32u, sa += 128u, dst += 32) *dst = lds32(sa);
-                    } else {                                 // larger than the staging: pack in place
-                        encode_wave_in_place<K, kDelta>(p.raw + d.begin, d.n, raw_hi, lane, rec + 1, d.nwords);
-                    }
-                }
-            }
-            __syncwarp();
-            if (back == 1u) break;
-        }
-        SEG_STAMP(6);
-        if (!live) break;
-        buf = buf + 1u == sl.nstage ? 0u : buf + 1u;
-    }
-    maxlane = __reduce_max_sync(0xffffffffu, maxlane);
-    if (sl.max_words && lane == 0 && maxw) {
-        atomicMax(sl.max_words, maxw);
-        atomicMax(sl.max_words + 1, (maxlane + 31u) >> 5);
-        if (novf) atomicAdd(sl.max_words + 2, novf);      // waves that took the in-place path (diagnostics)
-    }
 }
 
 // ======================================================================================
@@ -1752,6 +1198,16 @@ encode_multi_kernel(const EncodeParams p, const int dmask)
     pack_wave_streaming<K>(wave, wg.n, rec, smem, dmask);
 }
 
+// Launch geometry of the tile kernel.  Shared memory per CTA = two staging buffers of `stage` words per
+// worker warp (+ the pair table); a wave that outgrows its staging is packed a second time straight into
+// its record, so the staging should hold the batch's largest record: it is sized from the largest record
+// of the context's previous batch of the same shape (`words_hint`, + 1/16), else for 10 bits per sample.
+// More resident worker warps beat larger staging (measured, L = 7000: 2 x 12 warps 0.44 ms, 1 x 24 0.45,
+// 1 x 20 0.48, 1 x 12 0.65, 1 x 8 0.90), so the geometries are tried in that order and the first one
+// whose staging holds `want` words wins; without a hint the first geometry is taken with all the
+// staging it has room for.
+struct TileGeom { int workers, ctas; };
+
 template <int K>
 int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len, cudaStream_t st)
 {
@@ -1761,139 +1217,45 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
         encode_multi_kernel<K><<<p.nwaves, kEncMaxThreads, smem_multi, st>>>(p, md.delta ? -1 : 0);
         return 1;
     }
-    // large batches: one lane per wave (needs a worst-case sized scratch slot per wave)
-    if (md.lane_scratch && md.lane_slot_words) {
-        static DeviceOnce attr_lane;
-        const size_t smem_lane = (size_t)kLaneWarps * kLaneRingWords * 128;
-        if (attr_lane.first()) {
-            cudaFuncSetAttribute(encode_lane_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lane);
-            cudaFuncSetAttribute(encode_lane_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        }
-        const uint32_t ngroups = (p.nwaves + 31u) / 32u;
-        uint32_t nslices = (max_wave_len / 16u + kLaneSliceBlocks - 1u) / kLaneSliceBlocks;
-        if (nslices < 1u) nslices = 1u;
-        int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encode_lane_kernel<K>, kLaneWarps * 32, smem_lane);
-        if (occ < 1) occ = 1;
-        if (occ > 2) occ = 2;
-        uint32_t grid = (uint32_t)(occ * g_num_sms);
-        const uint32_t need = (ngroups + kLaneWarps - 1) / kLaneWarps;
-        if (grid > need) grid = need;
-        encode_lane_kernel<K><<<grid, kLaneWarps * 32, smem_lane, st>>>(p, md.lane_scratch, md.lane_slot_words, ngroups, nslices,
-                                                                      md.lane_state, md.lane_slice_done,
-                                                                      md.delta ? 0xFFFF0001u : 1u, md.delta ? 0xFFFFFFFFu : 0u);
-        return 1;
-    }
-    // the segment kernel: waves of kSegMinL .. kEncTileMaxL samples
-    {
-        static const bool seg_on = [] { const char *e = getenv("DRICE_ENC_SEG"); return e && atoi(e) != 0; }();
-        if (seg_on && max_wave_len >= kSegMinL) {
-            SegLaunch sl{};
-            // blocks of 16 samples per lane and piece: the whole wave in one piece when that needs <= kSegMaxBlocks
-            const uint32_t nb_wave = (max_wave_len + 15u + 15u) / 16u;                 // (+15: misalignment)
-            const uint32_t np = (nb_wave + 32u * kSegMaxBlocks - 1u) / (32u * kSegMaxBlocks);
-            sl.nbmax = ((nb_wave + np - 1u) / np + 31u) / 32u;
-            const uint32_t seg = sl.nbmax * 16u;
-            const uint32_t worst = (25u * max_wave_len + 31u) / 32u + 8u;
-            // words per record: the previous batch's largest (+ margin), else room for 10 bits per sample
-            uint32_t rec = md.seg_words_hint ? md.seg_words_hint + md.seg_words_hint / 16u + 16u
-                                             : (10u * max_wave_len + 31u) / 32u + 16u;
-            static const long stage_env = [] { const char *e = getenv("DRICE_ENC_STAGE_WORDS"); return e ? atol(e) : 0l; }();
-            if (stage_env > 0) rec = (uint32_t)stage_env;
-            if (rec > worst) rec = worst;
-            if (rec < 64u) rec = 64u;
-            sl.stage_words = (rec + 3u) & ~3u;
-            // a lane's ring: the previous batch's longest lane stream (+ margin), else room for 12 bits per
-            // sample; a power of two, at most the worst case of a segment
-            uint32_t lw = 16u;
-            const uint32_t lane_need = md.seg_lane_hint ? md.seg_lane_hint + md.seg_lane_hint / 8u + 3u : (12u * seg) / 32u + 3u;
-            const uint32_t lane_worst = (25u * seg + 31u) / 32u + 2u;
-            while (lw < lane_need && lw < lane_worst) lw <<= 1;
-            sl.lane_words = lw;
-            static const long nstage_env = [] { const char *e = getenv("DRICE_ENC_SEG_STAGES"); return e ? atol(e) : 0l; }();
-            sl.nstage = nstage_env == 2 ? 2u : (nstage_env == 3 ? 3u : (sl.stage_words <= 1024u ? 3u : 2u));
-            const size_t warp_bytes = (size_t)lw * 128u + (size_t)sl.nstage * sl.stage_words * 4u + 64u;
-            const size_t avail = (227u * 1024u) / 2u - 1024u - (size_t)lw * 128u;      // two CTAs per SM; static + alignment slack
-            static const long nw_env = [] { const char *e = getenv("DRICE_ENC_SEG_WARPS"); return e ? atol(e) : 0l; }();
-            uint32_t nw = (uint32_t)(avail / warp_bytes);
-            if (nw > (uint32_t)kSegMaxWorkers) nw = kSegMaxWorkers;
-            if (nw_env > 0 && (uint32_t)nw_env < nw) nw = (uint32_t)nw_env;
-            if (nw >= 2u) {
-                if (nw > p.nwaves) nw = p.nwaves;
-                sl.nworkers = nw;
-                sl.ntiles = (p.nwaves + nw - 1u) / nw;
-                sl.max_words = md.seg_max_words;
-                sl.mulx = 0xFFFF0001u;
-                sl.p16 = 65536u;
-                sl.p16mk = 65536u >> (K <= 7 ? K : 0);
-                sl.four = 4u;
-                static const long dbg_env = [] { const char *e = getenv("DRICE_ENC_SEG_DBG"); return e ? atol(e) : 0l; }();
-                sl.dbg = (uint32_t)dbg_env;
-                static const bool debug = getenv("DRICE_DEBUG") != nullptr;
-                if (debug)
-                    fprintf(stderr, "[drice] encode_seg K=%d L=%u waves=%u: %u workers/CTA, nbmax=%u, lane ring %u words, staging %u x %u words, "
-                                    "hints rec=%u lane=%u, smem %zu B\n", K, max_wave_len, p.nwaves, nw, sl.nbmax, lw, sl.nstage, sl.stage_words,
-                            md.seg_words_hint, md.seg_lane_hint, warp_bytes * nw + (size_t)lw * 128u);
-                const size_t smem = warp_bytes * nw + (size_t)lw * 128u;
-                auto launch_seg = [&](auto kernel, DeviceOnce &once) {
-                    if (once.first()) {
-                        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
-                        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-                    }
-                    int occ = 0;
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, (int)(nw + 1u) * 32, smem);
-                    if (occ < 1) occ = 1;
-                    uint32_t grid = (uint32_t)(device_sm_count() * occ);
-                    if (grid > sl.ntiles) grid = sl.ntiles;
-                    kernel<<<grid, (nw + 1u) * 32u, smem, st>>>(p, sl);
-                };
-                static const char *trace_path = getenv("DRICE_ENC_SEG_TRACE");
-                static long long *d_trace = nullptr;
-                const size_t trace_n = (size_t)kSegMaxWorkers * 16u * 8u;
-                if (trace_path && !d_trace) cudaMalloc((void **)&d_trace, trace_n * sizeof(long long));
-                if (trace_path && d_trace) cudaMemsetAsync(d_trace, 0, trace_n * sizeof(long long), st);
-                sl.trace = trace_path ? d_trace : nullptr;
-                static DeviceOnce once_d, once_n;
-                if (md.delta) launch_seg(encode_seg_kernel<K, true>, once_d);
-                else launch_seg(encode_seg_kernel<K, false>, once_n);
-                if (trace_path && d_trace) {                 // diagnostics only: synchronous
-                    std::vector<long long> h(trace_n);
-                    cudaStreamSynchronize(st);
-                    cudaMemcpy(h.data(), d_trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost);
-                    if (FILE *f = fopen(trace_path, "w")) {
-                        for (size_t w = 0; w < (size_t)nw; ++w)
-                            for (size_t i = 0; i < 16; ++i) {
-                                const long long *t = &h[(w * 16 + i) * 8];
-                                fprintf(f, "%zu %zu", w, i + 8);
-                                for (int k = 0; k < 8; ++k) fprintf(f, " %lld", t[k] ? t[k] - h[0] : -1ll);
-                                fprintf(f, "\n");
-                            }
-                        fclose(f);
-                    }
-                }
-                return 1;
-            }
-        }
-    }
-    // per-warp staging (two buffers per worker warp): room for ~10 bits per sample, at most the
-    // worst case; a wave that outgrows it is packed straight into its record in HBM.  Short
-    // waves: 12 worker warps per CTA, two CTAs per SM; longer ones: 8 worker warps (larger staging).
+    static const int lut_env = [] { const char *v = getenv("DRICE_ENC_LUT"); return v ? atoi(v) : 1; }();
+    static const int workers_env = [] { const char *v = getenv("DRICE_ENC_WORKERS"); return v ? atoi(v) : 0; }();
+    static const long stage_env = [] { const char *v = getenv("DRICE_ENC_STAGE_WORDS"); return v ? atol(v) : 0l; }();
+    const bool lut = LutConst<K>::kOk && md.delta && lut_env != 0;
+    const size_t table = lut ? lut_table_bytes<K, 1>() : 0;
     const uint32_t worst = (25u * max_wave_len + 31u) / 32u + 24u;
-    uint32_t stage = (10u * max_wave_len + 31u) / 32u + 24u;
-    const char *e = getenv("DRICE_ENC_STAGE_WORDS");
-    const bool twelve = !e && md.delta && stage <= 1120u;
-    if (e) stage = (uint32_t)atol(e);
-    else if (stage <= 1120u) stage = stage < 1088u ? stage : 1088u;
-    else stage = 1600u;
-    if (stage > worst) stage = worst;
-    if (stage < 64u) stage = 64u;
+    uint32_t want = md.words_hint ? md.words_hint + md.words_hint / 16u + 24u : (10u * max_wave_len + 31u) / 32u + 24u;
+    if (stage_env > 0) want = (uint32_t)stage_env;
+    if (want > worst) want = worst;
+    if (want < 64u) want = 64u;
+    // room of a geometry: (227 KB - 1 KB reserved per CTA) / CTAs - static shared memory - table
+    auto room_words = [&](TileGeom g) -> uint32_t {
+        const size_t per_cta = (size_t)(227 * 1024) / g.ctas - 1024 - 256 - table;
+        return (uint32_t)(per_cta / ((size_t)g.workers * 8)) & ~3u;
+    };
+    const TileGeom order[] = {{12, 2}, {24, 1}, {8, 2}, {8, 1}};
+    TileGeom geom = order[3];
+    bool found = false;
+    for (const TileGeom g : order) {
+        if ((!lut || !md.delta) && g.workers == 24) continue;          // (only the table kernel is built for 24 workers)
+        if (workers_env && g.workers != workers_env) continue;
+        if (room_words(g) >= want || (!md.words_hint && stage_env <= 0 && g.workers == 12)) { geom = g; found = true; break; }
+    }
+    if (!found && workers_env) for (const TileGeom g : order) if (g.workers == workers_env) { geom = g; break; }
+    uint32_t stage = room_words(geom) < want ? room_words(geom) : want;
+    if (!md.words_hint && stage_env <= 0) stage = room_words(geom) < worst ? room_words(geom) : worst;   // no hint: all the room
     stage = (stage + 3u) & ~3u;
+    if (stage > room_words(geom)) stage = room_words(geom);
+    {
+        static const bool debug = getenv("DRICE_DEBUG") != nullptr;
+        if (debug) fprintf(stderr, "[drice] encode_tile K=%d L=%u waves=%u: %d workers x %d CTAs, staging %u words (want %u, hint %u), %s front-end\n",
+                           K, max_wave_len, p.nwaves, geom.workers, geom.ctas, stage, want, md.words_hint, lut ? "table" : "arithmetic");
+    }
     auto launch = [&](auto kernel, DeviceOnce &attr_set, int nworkers) {
-        const size_t smem = (size_t)stage * 2 * nworkers * sizeof(uint32_t);   // two buffers per worker warp
+        const size_t smem = (size_t)stage * 2 * nworkers * sizeof(uint32_t) + table;   // two buffers per worker warp
         const int nthreads = (nworkers + 1) * 32;
         const uint32_t ntiles = (p.nwaves + nworkers - 1) / nworkers;
         if (attr_set.first()) {
-            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
             cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         }
         int occ = 0;
@@ -1901,12 +1263,20 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
         if (occ < 1) occ = 1;
         uint32_t grid = (uint32_t)(g_num_sms * occ);
         if (grid > ntiles) grid = ntiles;
-        kernel<<<grid, nthreads, smem, st>>>(p, stage, ntiles);
+        kernel<<<grid, nthreads, smem, st>>>(p, stage, ntiles, md.max_words);
     };
-    static DeviceOnce attr12, attr8, attr8n;                     // per K (this function is a template)
-    if (!md.delta) launch(encode_tile_kernel<K, 2, false, 8>, attr8n, 8);    // no delta (filter [1] / pre-filtered input)
-    else if (twelve) launch(encode_tile_kernel<K, 2, true, 12>, attr12, 12);
-    else launch(encode_tile_kernel<K, 2, true, 8>, attr8, 8);
+    static DeviceOnce a12, a8, a8n, t12, t24, t8;                // per K (this function is a template)
+    if constexpr (LutConst<K>::kOk) {
+        if (lut) {
+            if (geom.workers == 12) launch(encode_tile_kernel<K, 2, true, 12, 1>, t12, 12);
+            else if (geom.workers == 24) launch(encode_tile_kernel<K, 1, true, 24, 1>, t24, 24);
+            else launch(encode_tile_kernel<K, 2, true, 8, 1>, t8, 8);
+            return 1;
+        }
+    }
+    if (!md.delta) launch(encode_tile_kernel<K, 2, false, 8>, a8n, 8);    // no delta (filter [1] / pre-filtered input)
+    else if (geom.workers == 12) launch(encode_tile_kernel<K, 2, true, 12>, a12, 12);
+    else launch(encode_tile_kernel<K, 2, true, 8>, a8, 8);
     return 1;
 }
 

@@ -17,7 +17,6 @@ constexpr int      kSamplesPerThread = 16;   // one 32-byte aligned slot per thr
 constexpr uint32_t kEscapeQuotient   = 8;    // reference "giveup", src/deltaRice.c:203
 constexpr uint32_t kEscapeBits       = 25;   // 8 zeros + 1 + 16 value bits
 constexpr int      kEncMaxThreads    = 512;  // CTA size of the long-wave / redo kernels
-constexpr int      kEncWavesPerWarp  = 1;    // waves per worker warp and tile
 constexpr int      kEncTileMaxL      = 8192; // longest wave the warp-per-wave kernel takes
 
 // status flags
@@ -49,17 +48,10 @@ struct EncodeMode {
     // pre-filter mode: 1 = delta (src/deltaRice.c:53-62), 0 = none: the samples are Rice-coded as
     // they are (filter [1], or already filtered by prefilter_kernel)
     int             delta;
-    // lane-per-wave encoder (large batches, opt-in): scratch of nwaves slots of lane_slot_words words
-    // (worst case of a wave, multiple of 8); null = warp-per-wave tile kernel
-    uint32_t       *lane_scratch;
-    uint32_t        lane_slot_words;
-    uint32_t       *lane_state;         // [ntasks][6][32]: lane state parked between time slices
-    uint32_t       *lane_slice_done;    // [ntasks], zeroed: slices a task has finished
-    // segment encoder: words of the largest record the previous batch of this context produced
-    // (0 = unknown: room for 10 bits per sample), and where this launch reports its own
-    uint32_t        seg_words_hint;
-    uint32_t        seg_lane_hint;      // same for the longest per-lane stream
-    uint32_t       *seg_max_words;
+    // words of the largest record the context's previous batch of the same shape produced (0 = unknown):
+    // sizes the tile kernel's staging; the launch raises *max_words (device) with its own largest record
+    uint32_t        words_hint;
+    uint32_t       *max_words;
 };
 
 // generic pre-filter (src/deltaRice.c:64-74 / :91-102), taps by value

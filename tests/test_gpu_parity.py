@@ -129,17 +129,37 @@ def test_set_filter_rejects(codec):
     codec.set_filter(None)
 
 
-def test_lane_encoder_on_the_small_cases():
-    """Large batches are encoded by encode_lane_kernel (one lane per wave), small ones by
-    encode_tile_kernel (one warp per wave).  DRICE_ENC_LANE_MIN=1 (read once per process) sends
-    EVERY batch to the lane kernel: the edge-case suite must stay bit-exact there too."""
+def test_arithmetic_front_end_on_the_small_cases():
+    """For RiceParameter 2, 4 and 8 the tile encoder looks pair codes up in a shared-memory table; every
+    other parameter (and pre-filtered input) takes the arithmetic front-end.  DRICE_ENC_LUT=0 (read once per
+    process) sends EVERY batch through the arithmetic one: the edge-case suite must stay bit-exact there too."""
     import subprocess
     import sys
-    if os.environ.get("DRICE_ENC_LANE_MIN"):
+    if os.environ.get("DRICE_ENC_LUT"):
         pytest.skip("already running under the override")
-    env = dict(os.environ, DRICE_ENC_LANE_MIN="1")
+    env = dict(os.environ, DRICE_ENC_LUT="0")
     sel = ("single_chunk_host_path or single_chunk_h5z_filter or golden or ragged_batch or generic_filter_batch "
-           "or unaligned_pointers or many_chunks or readme_config or errors")
+           "or unaligned_pointers or many_chunks or readme_config or errors or full_size_c2")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", sel],
+                       env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout
+
+
+@pytest.mark.parametrize("workers,stage", [(12, 0), (24, 0), (8, 0), (12, 300), (8, 64)])
+def test_tile_geometries_and_small_staging(workers, stage):
+    """The tile encoder runs as 2 x 12, 1 x 24 or 2 x 8 worker warps per SM depending on the staging a wave
+    needs, and a wave that outgrows its staging is packed a second time straight into its record: force
+    each geometry (DRICE_ENC_WORKERS) and a staging far too small (DRICE_ENC_STAGE_WORDS) on cases of
+    every Rice parameter class."""
+    import subprocess
+    import sys
+    if os.environ.get("DRICE_ENC_WORKERS"):
+        pytest.skip("already running under the override")
+    env = dict(os.environ, DRICE_ENC_WORKERS=str(workers))
+    if stage:
+        env["DRICE_ENC_STAGE_WORDS"] = str(stage)
+    sel = "golden or ragged_batch or unaligned_pointers or readme_config or rice_parameter_sweep"
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", sel],
                        env=env, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]

@@ -23,4 +23,14 @@ for _ in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); codec.encode_device_async(x, off, M, L, out, d_boff, d_status); e1.record()
     torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
-print(f"dbg={os.environ.get('DRICE_ENC_SEG_DBG','0')} encode median {np.median(ts):.3f} ms best {min(ts):.3f} (incl. prep kernel) bytes {int(d_boff[-1])}")
+nb = int(d_boff[-1])
+ok = int(d_status[0]) == 0
+# checksum of the stream (compare across variants) and the round trip
+w = out[:nb].view(torch.int32).to(torch.int64)
+chk = int((w * (torch.arange(w.numel(), device="cuda") % 65521 + 1)).sum())
+y = torch.empty_like(x)
+codec.decode_device_async(out[:nb], d_boff.cpu().numpy().astype(np.uint64), off, M, L, y, d_status)
+torch.cuda.synchronize()
+rt = bool(torch.equal(x, y)) and int(d_status[0]) == 0
+print(f"lut={os.environ.get('DRICE_ENC_LUT','-')} waves={n_waves} L={L} M={M} encode median {np.median(ts):.3f} ms best {min(ts):.3f} (incl. prep kernel) "
+      f"bytes {nb} chk {chk} status_ok {ok} roundtrip {rt}")
