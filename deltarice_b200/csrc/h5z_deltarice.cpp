@@ -25,6 +25,7 @@
 #endif
 
 #include <dlfcn.h>
+#include <link.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -235,7 +236,25 @@ size_t H5Z_filter_deltarice(unsigned flags, size_t cd_nelmts, const unsigned cd_
 int deltarice_register_h5filter(void)
 {
     typedef herr_t (*H5Zregister_t)(const void *);
+    // libhdf5 is resolved from the running process (no link-time dependency).  The global scope first
+    // (C programs linked against libhdf5, LD_PRELOAD); then every loaded object whose name contains
+    // "libhdf5": Python extension modules are loaded RTLD_LOCAL and pull in a private, often hashed
+    // libhdf5-*.so whose symbols RTLD_DEFAULT does not see.
     H5Zregister_t reg = (H5Zregister_t)dlsym(RTLD_DEFAULT, "H5Zregister");
+    if (!reg) {
+        struct Find { H5Zregister_t fn; } find{nullptr};
+        dl_iterate_phdr([](struct dl_phdr_info *info, size_t, void *data) -> int {
+            Find *f = (Find *)data;
+            const char *name = info->dlpi_name;
+            if (!name || !strstr(name, "libhdf5") || strstr(name, "libhdf5_hl")) return 0;
+            if (void *h = dlopen(name, RTLD_NOLOAD | RTLD_LAZY)) {
+                f->fn = (H5Zregister_t)dlsym(h, "H5Zregister");
+                dlclose(h);                              // (RTLD_NOLOAD took a reference)
+            }
+            return f->fn != nullptr;
+        }, &find);
+        reg = find.fn;
+    }
     if (!reg) {
         fprintf(stderr, "deltarice_register_h5filter: no libhdf5 in this process (H5Zregister not found)\n");
         return -1;

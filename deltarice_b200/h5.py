@@ -32,8 +32,19 @@ def plugin_path() -> str:
 
 
 def register_h5_filter() -> int:
-    """Returns H5Zregister's herr_t (< 0: failed / no libhdf5 loaded in this process)."""
+    """Returns H5Zregister's herr_t (< 0: failed / no libhdf5 loaded in this process).  The library looks
+    for H5Zregister in the global scope first and then in every loaded object whose name contains
+    "libhdf5" (h5py's extension modules pull libhdf5 in RTLD_LOCAL, wheels under a hashed name)."""
     return int(_lib.load().deltarice_register_h5filter())
+
+
+def h5py_loaded() -> bool:
+    """True when h5py can be imported (its libhdf5 is then in the process)."""
+    try:
+        import h5py  # noqa: F401
+        return True
+    except Exception:  # noqa: BLE001
+        return False
 
 
 def apply_filter(data: bytes, cd_values=(), reverse: bool = False) -> bytes:
@@ -131,14 +142,23 @@ def decode_dataset_chunks(codec, chunk_bytes, shape, chunks, compression_opts=()
 
 
 def _auto_register():
-    try:
-        import h5py  # noqa: F401
-    except Exception:
+    """With h5py in the process the filter is registered at import, as the reference module does
+    (src/h5.pyx:61).  A failure is reported, not swallowed: HDF5_PLUGIN_PATH=plugin_path() is the route
+    that does not depend on finding h5py's libhdf5."""
+    if not h5py_loaded():
         return
+    ret = -1
     try:
-        register_h5_filter()
-    except Exception:
-        pass
+        ret = register_h5_filter()
+    except Exception as e:  # noqa: BLE001
+        import warnings
+        warnings.warn(f"deltarice_b200.h5: registering filter {H5FILTER} failed ({e!r}); "
+                      f"set HDF5_PLUGIN_PATH={plugin_path()} instead", RuntimeWarning)
+        return
+    if ret < 0:
+        import warnings
+        warnings.warn(f"deltarice_b200.h5: H5Zregister was not found or refused filter {H5FILTER} (ret {ret}); "
+                      f"set HDF5_PLUGIN_PATH={plugin_path()} instead", RuntimeWarning)
 
 
 _auto_register()

@@ -101,6 +101,23 @@ def encode_chunk(x: np.ndarray, M: int = 8, L: int | None = None, mt: bool = Fal
     return out[:n].copy()
 
 
+def encode_chunk_cd(x: np.ndarray, cd=()) -> np.ndarray:
+    """encode_chunk driven by a compression_opts tuple as h5py passes it (parseCD_VALUES,
+    src/deltaRice.c:248-291): () -> M=8, whole chunk; (M,); (M, L); (M, L, filter_len, taps...)."""
+    cd = tuple(int(v) for v in cd)
+    M = cd[0] if len(cd) >= 1 else 8
+    L = None
+    if len(cd) >= 2:
+        Lv = cd[1] & 0xFFFFFFFF
+        L = None if Lv == 0xFFFFFFFF else Lv
+    filt = None
+    if len(cd) >= 3:
+        filt = [((v & 0xFFFFFFFF) ^ 0x80000000) - 0x80000000 for v in cd[3:3 + cd[2]]]
+        if filt == [1, -1]:
+            filt = None
+    return encode_chunk(x, M, L, filt=filt)
+
+
 def decode_chunk(words: np.ndarray, M: int = 8, L: int | None = None, mt: bool = False, filt=None) -> np.ndarray:
     """uint32 stream words of one chunk -> int16[total] (reference src/deltaRice.c:301-341).
     `filt`: pre-filter taps to invert (reference :91-102); None = the delta filter."""

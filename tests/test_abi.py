@@ -108,3 +108,16 @@ def test_chunk_grid_follows_hdf5_order():
     g = h5.chunk_grid((50, 333), (16, 128))
     assert len(g) == 4 * 3 and g[0] == (0, 0) and g[1] == (0, 128) and g[3] == (16, 0) and g[-1] == (48, 256)
     assert h5.chunk_grid((7,), (3,)) == [(0,), (3,), (6,)]
+
+
+def test_reference_module_name_imports():
+    """Reference user scripts do `import deltaRice.h5` (README.md:65-91, tests/test.py:1-2): the shim
+    package carries the reference module's names (src/h5.pyx:27, :55)."""
+    import deltaRice.h5 as m
+    assert m.H5FILTER == 32025
+    assert callable(m.register_h5_filter)
+    import deltarice_b200.h5 as h
+    if not h.h5py_loaded():                              # no libhdf5 here: registration must FAIL loudly
+        import pytest
+        with pytest.raises(RuntimeError):
+            m.register_h5_filter()
