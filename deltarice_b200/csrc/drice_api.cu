@@ -657,15 +657,18 @@ extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_co
     }
     if (!d_comp) return fail(ctx, DRICE_E_PARAM, "null input");
     const size_t nw = g.nwaves;
-    const size_t scratch = nw * (8 + 8 + 4) + 64 + 16;
+    // scratch: [parse ticket, 16 B][chain state of the long-wave parser] (zeroed) | wave tables
+    const size_t long_bytes = parse_long_state_bytes(g.nwaves, g.max_wave);
+    const size_t zeroed = 16 + long_bytes;
+    const size_t scratch = zeroed + nw * (8 + 8 + 4) + 64 + 16;
     if (scratch > ctx->d_scratch.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
     DR_CUDA(ctx, ctx->d_scratch.reserve(scratch));
     uint64_t *d_soff, *d_woff64;
     uint32_t *d_wave_off;
     rc = upload_tables(ctx, off, woff.data(), g.wave_off.data(), nchunks, st, &d_soff, &d_woff64, &d_wave_off,
-                       ctx->d_scratch.p, 16, d_status);      // (16 bytes: the parse ticket)
+                       ctx->d_scratch.p, zeroed, d_status);
     if (rc) return rc;
-    uint64_t *wave_in = (uint64_t *)((char *)ctx->d_scratch.p + 16);
+    uint64_t *wave_in = (uint64_t *)((char *)ctx->d_scratch.p + zeroed);
     uint64_t *wave_out = wave_in + nw;
     uint32_t *wave_n = (uint32_t *)(wave_out + nw);
 
@@ -707,6 +710,7 @@ extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_co
     pp.max_n = g.max_wave;
     pp.k = k;
     pp.identity = ctx->filter_mode != 0;
+    pp.long_state = long_bytes ? (unsigned long long *)((char *)ctx->d_scratch.p + 16) : nullptr;
     // widest store that every wave start allows
     int store_bytes = (int)(g.align_samples * 2);
     while (store_bytes > 2 && (reinterpret_cast<uintptr_t>(d_out) & (uintptr_t)(store_bytes - 1))) store_bytes >>= 1;

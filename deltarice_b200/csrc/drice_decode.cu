@@ -961,6 +961,198 @@ __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2) parse_wide_kernel(cons
     }
 }
 
+// ------------------------------------------------------------------------------------
+// parse, long waves (> 8192 samples) in small batches: several CTAs per wave
+// ------------------------------------------------------------------------------------
+// The reference's long-wave configurations (docs/Performance.md:27-47: 32 x 81920, 32 x 500000) and its
+// DEFAULT option tuple (WaveformLength = -1: the whole chunk is one wave) give a handful of waves of up
+// to millions of samples: one lane per wave would decode them on one warp.  The run decomposition of
+// parse_wide_kernel carries over: the record is cut into SEGMENTS of kWideMaxWords words, one work item
+// (wave, segment) per CTA, items handed out in order by a ticket.  A segment does everything that does
+// not depend on its predecessor first - the transition functions of its runs, composed into the
+// segment's own function (entry offset -> exit offset) for all 32 entry offsets at once - and then takes
+// part in two short chains along the wave: the entry offset (one lookup in its function per link), and
+// after counting its codes, the sample index and running value at its start.  A link is one global
+// round trip; an item only ever waits for the item ticketed right before it, which is running or done.
+constexpr int kLongGroups = 32;                          // the runs of a segment are composed in 32 groups, one per warp
+constexpr unsigned long long kLongReady = 1ull << 63;
+
+__device__ __forceinline__ unsigned long long long_wait(const unsigned long long *p)
+{
+    unsigned long long v;
+    do {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        if (!(v & kLongReady)) __nanosleep(100);
+    } while (!(v & kLongReady));
+    return v;
+}
+__device__ __forceinline__ void long_post(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v | kLongReady) : "memory");
+}
+// words a record of n samples can have at most (25 bits per sample)
+__host__ __device__ __forceinline__ uint64_t long_worst_words(uint64_t n) { return (25ull * n + 31ull) / 32ull; }
+
+template <bool IDENT>
+__global__ void __launch_bounds__(kWideThreads, 1)
+parse_long_kernel(const ParseParams p, const uint32_t segs_per_wave, const uint32_t nitems, unsigned long long *const state)
+{
+    constexpr int NT = kWideThreads;
+    extern __shared__ __align__(16) uint32_t wsm[];
+    uint32_t *words = wsm;                                       // kWideMaxWords + 4 (the last run looks past the segment)
+    uint32_t *lut = words + kWideMaxWords + 4;
+    uint32_t *cnt = lut + (1 << kWideLutBits);
+    uint32_t *dsum = cnt + NT;
+    uint8_t *T = reinterpret_cast<uint8_t *>(dsum + NT);         // [kWideMaxRuns][32]: transition functions, then the 32 paths
+    uint8_t *E = T + kWideMaxRuns * 32;                          // [kWideMaxRuns + 16] entry offsets
+    uint8_t *G = E + kWideMaxRuns + 16;                          // [kLongGroups][32] group functions
+    uint8_t *GE = G + kLongGroups * 32;                          // [kLongGroups][32] entry of a group for every segment entry
+    __shared__ uint32_t s_warp_c[NT / 32], s_warp_d[NT / 32];
+    __shared__ uint32_t s_item, s_ein, s_acc0;
+    __shared__ unsigned long long s_idx0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k = p.k;
+    const uint32_t kmask = (1u << k) - 1u;
+    for (uint32_t i = threadIdx.x; i < (1u << kWideLutBits); i += NT) lut[i] = make_lut_entry(i, k, kWideLutBits);
+
+    for (;;) {
+        __syncthreads();                                         // (previous item done with shared memory; LUT built)
+        if (threadIdx.x == 0) s_item = atomicAdd(p.ticket, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= nitems) break;
+        const uint32_t g = item / segs_per_wave, sg = item - g * segs_per_wave;
+        const uint32_t n = p.wave_n[g];
+        if (n == 0) continue;
+        const uint64_t rec = p.wave_in[g];
+        const uint32_t nw = p.comp[rec];
+        if (nw == 0 || (uint64_t)nw > long_worst_words(n) || rec + 1 + nw > p.comp_words) {   // (the same verdict in every segment)
+            if (threadIdx.x == 0 && sg == 0) atomicOr(p.status, kErrStream);
+            continue;
+        }
+        const uint64_t w0 = (uint64_t)sg * kWideMaxWords;
+        if (w0 >= nw) continue;                                  // the record has fewer segments
+        const uint32_t nseg = (uint32_t)((nw - w0) < (uint64_t)kWideMaxWords ? (nw - w0) : (uint64_t)kWideMaxWords);
+        const bool last_seg = w0 + nseg == nw;
+        int16_t *out = p.out + p.wave_out[g];
+        for (uint32_t i = threadIdx.x; i < nseg + 4; i += NT) words[i] = (w0 + i < nw) ? p.comp[rec + 1 + w0 + i] : 0u;
+        __syncthreads();
+        const uint32_t nruns = (nseg + kWideRunWords - 1) / kWideRunWords;
+        // ---- transition function of every run: lane o enters at bit offset o ---------------------
+        for (uint32_t r = warp; r < nruns; r += NT / 32) {
+            const uint32_t end = (r + 1) * (kWideRunWords * 32);
+            uint32_t pos = r * (kWideRunWords * 32) + (uint32_t)lane;
+            while (pos < end) pos += wide_decode_at(words, lut, pos, k, kmask).len;
+            T[r * 32 + lane] = (uint8_t)(pos - end);             // < 25
+        }
+        __syncthreads();
+        // ---- group functions: warp w walks its runs for all 32 entry offsets, leaving the paths in T ---
+        const uint32_t gr = (nruns + kLongGroups - 1) / kLongGroups;
+        {
+            const uint32_t ra = warp * gr, rb = min(ra + gr, nruns);
+            uint32_t e = (uint32_t)lane;
+            for (uint32_t r = ra; r < rb; ++r) {
+                const uint32_t x = T[r * 32 + e];
+                __syncwarp();
+                T[r * 32 + lane] = (uint8_t)e;                   // entry of path `lane` at run r
+                __syncwarp();
+                e = x;
+            }
+            G[warp * 32 + lane] = (uint8_t)e;
+        }
+        __syncthreads();
+        // ---- the segment's function, then chain 1: the entry offset ------------------------------
+        if (warp == 0) {
+            uint32_t e = (uint32_t)lane;
+            for (int w = 0; w < kLongGroups; ++w) {
+                GE[w * 32 + lane] = (uint8_t)e;
+                e = G[w * 32 + e];
+            }
+            // e = exit offset when the segment is entered at offset `lane`
+            uint32_t ein = 0;
+            if (lane == 0 && sg != 0) ein = (uint32_t)(long_wait(state + 2 * (size_t)(item - 1)) & 31u);
+            ein = __shfl_sync(0xffffffffu, ein, 0);
+            const uint32_t eout = __shfl_sync(0xffffffffu, e, (int)ein);
+            if (lane == 0) {
+                long_post(state + 2 * (size_t)item, eout);
+                s_ein = ein;
+            }
+        }
+        __syncthreads();
+        const uint32_t ein = s_ein;
+        for (uint32_t r = threadIdx.x; r < nruns; r += NT) E[r] = T[r * 32 + GE[(r / gr) * 32 + ein]];
+        __syncthreads();
+        // ---- every thread takes consecutive runs: codes and delta sum first ---------------------
+        const uint32_t rpt = (nruns + NT - 1) / NT;
+        const uint32_t r0 = threadIdx.x * rpt, r1 = min(r0 + rpt, nruns);
+        uint32_t c = 0, dsm = 0;
+        for (uint32_t r = r0; r < r1; ++r) {
+            const uint32_t end = (r + 1) * (kWideRunWords * 32);
+            uint32_t pos = r * (kWideRunWords * 32) + E[r];
+            while (pos < end) {
+                const WideCode cd = wide_decode_at(words, lut, pos, k, kmask);
+                pos += cd.len;
+                ++c;
+                dsm += (uint32_t)cd.delta;
+            }
+        }
+        uint32_t ic = c, id = dsm;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t tc = __shfl_up_sync(0xffffffffu, ic, d), td = __shfl_up_sync(0xffffffffu, id, d);
+            if (lane >= d) { ic += tc; id += td; }
+        }
+        if (lane == 31) { s_warp_c[warp] = ic; s_warp_d[warp] = id; }
+        __syncthreads();
+        uint32_t bc = 0, bd = 0, total = 0, dtotal = 0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) {
+            if (w < warp) { bc += s_warp_c[w]; bd += s_warp_d[w]; }
+            total += s_warp_c[w];
+            dtotal += s_warp_d[w];
+        }
+        // ---- chain 2: sample index and running value at the segment's start ----------------------
+        if (threadIdx.x == 0) {
+            unsigned long long idx0 = 0;
+            uint32_t acc0 = 0;
+            if (sg != 0) {
+                const unsigned long long v = long_wait(state + 2 * (size_t)(item - 1) + 1);
+                idx0 = (v >> 16) & 0x7FFFFFFFFFFFull;
+                acc0 = (uint32_t)(v & 0xFFFFu);
+            }
+            long_post(state + 2 * (size_t)item + 1, ((idx0 + total) << 16) | ((acc0 + dtotal) & 0xFFFFu));
+            s_idx0 = idx0;
+            s_acc0 = acc0;
+        }
+        __syncthreads();
+        const unsigned long long idx0 = s_idx0;
+        unsigned long long idx = idx0 + bc + ic - c;             // sample index of the thread's first code
+        uint32_t acc = s_acc0 + bd + id - dsm;                   // running sample before it (src/deltaRice.c:84-89)
+        bool bad = threadIdx.x == 0 && ((last_seg && idx0 + total < n) || (!last_seg && idx0 + total >= n));
+        // ---- the samples --------------------------------------------------------------------------
+        for (uint32_t r = r0; r < r1 && idx < n; ++r) {
+            const uint32_t end = (r + 1) * (kWideRunWords * 32);
+            uint32_t pos = r * (kWideRunWords * 32) + E[r];
+            while (pos < end && idx < n) {
+                const WideCode cd = wide_decode_at(words, lut, pos, k, kmask);
+                pos += cd.len;
+                acc += (uint32_t)cd.delta;
+                bad |= !cd.valid;
+                out[idx] = (int16_t)(IDENT ? (uint32_t)cd.delta : acc);
+                ++idx;
+                if (idx == n) bad |= !last_seg || ((pos + 31u) >> 5) != nseg;   // the codes must end inside the record's last word
+            }
+        }
+        if (bad) atomicOr(p.status, kErrStream);
+    }
+}
+
+// work items of parse_long_kernel for a batch (0: the batch does not take that path)
+uint32_t parse_long_segments(uint32_t max_n)
+{
+    return (uint32_t)((long_worst_words(max_n) + kWideMaxWords - 1) / kWideMaxWords);
+}
+
 // warps per SM: as many as fit, trimmed so that the last round of warp tasks is nearly full
 int pick_parse_warps(uint32_t ngroups, int sms, int max_warps)
 {
@@ -995,6 +1187,21 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
         if (wide < 0) {
             const char *e = getenv("DRICE_PARSE_WIDE");
             wide = e ? atol(e) : (long)kWideMaxWaves;
+        }
+        if ((long)p.nwaves <= wide && p.max_n > 8192u && p.long_state) {
+            static DeviceOnce lattr;
+            const size_t lsmem = (size_t)(kWideMaxWords + 4 + (1 << kWideLutBits) + 2 * kWideThreads) * 4 +
+                                 (size_t)kWideMaxRuns * 32 + kWideMaxRuns + 16 + 2 * kLongGroups * 32 + 16;
+            if (lattr.first()) {
+                cudaFuncSetAttribute(parse_long_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
+                cudaFuncSetAttribute(parse_long_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
+            }
+            const uint32_t segs = parse_long_segments(p.max_n);
+            const uint64_t nitems = (uint64_t)p.nwaves * segs;
+            const uint32_t lgrid = nitems < (uint64_t)g_dec_sms ? (uint32_t)nitems : (uint32_t)g_dec_sms;
+            if (p.identity) parse_long_kernel<true><<<lgrid, kWideThreads, lsmem, st>>>(p, segs, (uint32_t)nitems, p.long_state);
+            else            parse_long_kernel<false><<<lgrid, kWideThreads, lsmem, st>>>(p, segs, (uint32_t)nitems, p.long_state);
+            return 1;
         }
         if ((long)p.nwaves <= wide && p.max_n <= 8192u) {
             static DeviceOnce wattr;
@@ -1061,6 +1268,20 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
 }
 
 }  // namespace
+
+// zeroed state (bytes) parse_long_kernel needs for a batch; 0 when the batch does not take that path
+size_t parse_long_state_bytes(uint32_t nwaves, uint32_t max_n)
+{
+    static long wide = -1;
+    if (wide < 0) {
+        const char *e = getenv("DRICE_PARSE_WIDE");
+        wide = e ? atol(e) : (long)kWideMaxWaves;
+    }
+    if ((long)nwaves > wide || max_n <= 8192u) return 0;
+    const uint64_t items = (uint64_t)nwaves * parse_long_segments(max_n);
+    if (items >= (1ull << 31)) return 0;
+    return (size_t)items * 16;
+}
 
 int launch_locate(const LocateParams &p, cudaStream_t st)
 {

@@ -92,6 +92,7 @@ struct ParseParams {
     uint32_t        smem_bytes;         // dynamic shared memory of the launch (set by the launcher)
     int             k;
     int             identity;           // 1: write the decoded values themselves (no inverse delta)
+    unsigned long long *long_state;     // zeroed, parse_long_state_bytes(): chain state of the long-wave parser (or null)
 };
 
 // ---- per-device launch state ------------------------------------------------------------------
@@ -173,6 +174,7 @@ int launch_locate(const LocateParams &p, cudaStream_t st);
 bool locate_scan_applies(uint32_t L, int k, uint64_t max_chunk_words, size_t nchunks, size_t *scratch_bytes);
 int launch_locate_scan(const LocateParams &p, int k, uint64_t max_chunk_words, void *scratch, cudaStream_t st);
 int launch_parse(const ParseParams &p, int store_bytes, cudaStream_t st);
+size_t parse_long_state_bytes(uint32_t nwaves, uint32_t max_n);
 // out[i] = sum_j in[i-j] * f[j] per wave (mod 2^16); in != out
 int launch_prefilter(const FilterParams &p, const int16_t *in, int16_t *out, uint64_t max_chunk_samples, cudaStream_t st);
 // in place: y[i] = (d[i] - sum_{j>=1} y[i-j] * f[j]) / f[0] per wave

@@ -293,6 +293,45 @@ def test_errors(codec, oracle):
     assert np.array_equal(codec.decode_host(s.view(np.uint8), None, None, 8, 7000), x)
 
 
+@pytest.mark.parametrize("M,L,sizes,sigma", [
+    (8, 81920, [32 * 81920], 10.0),                 # reference docs/Performance.md:27: nEDM-like chunk
+    (8, 500000, [3 * 500000 + 12345], 30.0),        # NOPTREX-like waves, ragged last wave
+    (8, None, [1400000], 10.0),                     # the reference's DEFAULT options: the whole chunk is one wave
+    (4, 8193, [8193 * 5, 8193 * 2 + 77, 1], 3.0),   # just past the tile kernels' 8192 samples
+    (16, 20000, [20000 * 7], 3000.0),               # escape dominated: 25-bit codes, many segments per wave
+    (1, 30000, [30000 * 2], 0.7),                   # RiceParameter 1
+])
+def test_long_waves(codec, oracle, M, L, sizes, sigma):
+    """Waves longer than 8192 samples in small batches: encode_multi_kernel and parse_long_kernel (several
+    CTAs per wave, chained along the record).  Bit-exact against the oracle, exact round trip."""
+    r = np.random.default_rng(77)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    x = np.clip(np.rint(np.cumsum(r.normal(0, sigma, int(off[-1]))) % 3000 - 1500 + r.normal(0, sigma, int(off[-1]))),
+                -32768, 32767).astype(np.int16)
+    want, wboff = _oracle_batch(oracle, x, off, M, L)
+    got, boff = codec.encode_host(x, off, M, L)
+    assert np.array_equal(boff, wboff)
+    assert np.array_equal(got.view(np.uint32), want)
+    assert np.array_equal(codec.decode_host(got, boff, off, M, L), x)
+    # the oracle's stream decodes as well (the parser does not rely on our encoder)
+    assert np.array_equal(codec.decode_host(want.view(np.uint8), wboff, off, M, L), x)
+
+
+def test_long_wave_errors(codec, oracle):
+    import deltarice_b200 as d
+    x = np.random.default_rng(5).normal(0, 20, 3 * 40000).astype(np.int16)
+    s = oracle.encode_chunk(x, 8, 40000)
+    assert np.array_equal(codec.decode_host(s.view(np.uint8), None, None, 8, 40000), x)
+    for bad in (s[:-5], np.concatenate([s[:20000], s[20001:]])):     # truncated; a word missing inside a record
+        with pytest.raises(d.DeltaRiceError):
+            codec.decode_host(np.ascontiguousarray(bad).view(np.uint8), None, np.array([0, x.size], dtype=np.uint64), 8, 40000)
+    flip = s.copy()
+    flip[30000] = 0                                                  # a run of 32 zero bits: not a code
+    with pytest.raises(d.DeltaRiceError):
+        codec.decode_host(flip.view(np.uint8), None, None, 8, 40000)
+    assert np.array_equal(codec.decode_host(s.view(np.uint8), None, None, 8, 40000), x)
+
+
 def test_full_size_c2_roundtrip_and_sampled_parity(codec, oracle):
     """BASELINE config C2 at full size (153 391 Nab-like waves of 3500, M=4, ~1 GB): device
     round trip decode(encode(x)) == x, compression ratio, and byte parity with the oracle on
