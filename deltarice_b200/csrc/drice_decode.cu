@@ -333,6 +333,30 @@ __global__ void __launch_bounds__(kScanThreads) scan_headers_kernel(const ScanPa
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     const uint32_t span = g.hi - g.lo;
+    // tiles inside the chunk (all but its first and last): no position checks, every load in flight at once
+    if (t0 > (int64_t)g.wb && t0 + kScanTileWords <= (int64_t)g.we && (uint64_t)t0 + kScanTileWords <= p.comp_words) {
+        constexpr int NV = kScanTileWords / 4 / kScanThreads;
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.comp + t0) + threadIdx.x;
+        uint4 v[NV];
+#pragma unroll
+        for (int r = 0; r < NV; ++r) v[r] = __ldg(src + r * kScanThreads);
+        const uint32_t rel0 = (uint32_t)((uint64_t)t0 - g.wb) + 4u * threadIdx.x;      // position relative to the chunk's first word
+        const uint64_t room = g.we - g.wb;                                             // a record must end inside the chunk
+#pragma unroll
+        for (int r = 0; r < NV; ++r) {
+            const uint32_t x[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+            if ((x[0] - g.lo <= span) | (x[1] - g.lo <= span) | (x[2] - g.lo <= span) | (x[3] - g.lo <= span)) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t rel = rel0 + 4u * (uint32_t)(r * kScanThreads) + (uint32_t)e;
+                    if (x[e] - g.lo <= span && (uint64_t)rel + 1 + x[e] <= room) {
+                        const uint32_t at = atomicAdd(&s_n, 1u);
+                        if (at < (uint32_t)kScanCap) s_list[at] = rel;
+                    }
+                }
+            }
+        }
+    } else
 #pragma unroll
     for (int r = 0; r < kScanTileWords / 4 / kScanThreads; ++r) {
         const int64_t b = t0 + 4ll * (r * kScanThreads + (int)threadIdx.x);
@@ -345,12 +369,17 @@ __global__ void __launch_bounds__(kScanThreads) scan_headers_kernel(const ScanPa
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = (b + e >= 0 && (uint64_t)(b + e) < p.comp_words) ? p.comp[b + e] : 0xFFFFFFFFu;
         }
+        // candidates are rare (one word in a few hundred): one cheap range test per word, everything else
+        // (64-bit position checks) only for the words that pass it - the kernel is ALU bound otherwise
+        const bool c0 = x[0] - g.lo <= span, c1 = x[1] - g.lo <= span, c2 = x[2] - g.lo <= span, c3 = x[3] - g.lo <= span;
+        if (c0 | c1 | c2 | c3) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int64_t i = b + e;
-            if (i > (int64_t)g.wb && i < (int64_t)g.we && x[e] - g.lo <= span && (uint64_t)i + 1 + x[e] <= g.we) {
-                const uint32_t at = atomicAdd(&s_n, 1u);
-                if (at < (uint32_t)kScanCap) s_list[at] = (uint32_t)((uint64_t)i - g.wb);
+            for (int e = 0; e < 4; ++e) {
+                const int64_t i = b + e;
+                if (x[e] - g.lo <= span && i > (int64_t)g.wb && i < (int64_t)g.we && (uint64_t)i + 1 + x[e] <= g.we) {
+                    const uint32_t at = atomicAdd(&s_n, 1u);
+                    if (at < (uint32_t)kScanCap) s_list[at] = (uint32_t)((uint64_t)i - g.wb);
+                }
             }
         }
     }
