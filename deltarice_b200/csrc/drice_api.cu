@@ -92,6 +92,11 @@ struct drice_ctx {
     DevBuf d_tab;                        // chunk tables
     DevBuf d_scratch;                    // look-back words / wave tables, ticket, status
     cudaEvent_t ev_tab = nullptr;        // tables uploaded (h_tab reusable)
+    // the scratch (tickets, look-back words, wave tables, scan candidates) is one set per context: a call
+    // enqueued on ANOTHER stream than the previous one first waits for that call's last kernel
+    cudaEvent_t ev_last = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool have_last = false;
     bool ev_tab_pending = false;
 
     // synchronous-call helpers
@@ -210,6 +215,8 @@ int upload_tables(drice_ctx *ctx, const uint64_t *t0, const uint64_t *t1, const 
 {
     const size_t n1 = nchunks + 1;
     const size_t bytes = n1 * 8 * 2 + n1 * 4;
+    // (first device work of every call) a different stream than the previous call's: order behind it
+    if (ctx->have_last && ctx->last_stream != st) DR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_last, 0));
     if (ctx->ev_tab_pending) {
         DR_CUDA(ctx, cudaEventSynchronize(ctx->ev_tab));
         ctx->ev_tab_pending = false;
@@ -283,6 +290,8 @@ struct TimedScope {
 int status_to_error(drice_ctx *ctx, uint32_t status)
 {
     if (status == 0) return DRICE_OK;
+    if (status & kErrInternal)
+        return fail(ctx, DRICE_E_CUDA, "internal error: the parser's shared-memory layout does not match its launch (not a stream problem)");
     if (status & kErrCapacity) return fail(ctx, DRICE_E_CAPACITY, "output buffer too small for the compressed batch");
     if (status & kErrTotal) return fail(ctx, DRICE_E_STREAM, "chunk stream's sample count differs from the expected chunk size");
     return fail(ctx, DRICE_E_STREAM, "malformed Delta-Rice stream");
@@ -393,6 +402,7 @@ extern "C" int drice_create(drice_ctx **out, int device)
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
               copy_streams(device, &ctx->s_in, &ctx->s_out) &&
               cudaEventCreateWithFlags(&ctx->ev_tab, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_last, cudaEventDisableTiming) == cudaSuccess &&
               cudaMalloc((void **)&ctx->d_hint, 16) == cudaSuccess && cudaMemset(ctx->d_hint, 0, 16) == cudaSuccess &&
               cudaMallocHost((void **)&ctx->h_hint, 16) == cudaSuccess;
     if (ok) ctx->h_hint[0] = ctx->h_hint[1] = 0;
@@ -433,6 +443,7 @@ extern "C" void drice_destroy(drice_ctx *ctx)
     if (ctx->h_hint) cudaFreeHost((void *)ctx->h_hint);
     if (ctx->h_sync) cudaFreeHost(ctx->h_sync);
     if (ctx->ev_tab) cudaEventDestroy(ctx->ev_tab);
+    if (ctx->ev_last) cudaEventDestroy(ctx->ev_last);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -589,6 +600,9 @@ extern "C" int drice_encode_batch_dev_async(drice_ctx *ctx, const int16_t *d_raw
     if (nl < 0) return fail(ctx, DRICE_E_PARAM, "unsupported RiceParameter");
     ctx->launches += (uint64_t)nl;
     DR_CUDA(ctx, cudaGetLastError());
+    DR_CUDA(ctx, cudaEventRecord(ctx->ev_last, st));
+    ctx->last_stream = st;
+    ctx->have_last = true;
     return DRICE_OK;
 }
 
@@ -735,6 +749,9 @@ extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_co
         ctx->launches += (uint64_t)launch_postfilter(fp, d_out, max_waves, st);
     }
     DR_CUDA(ctx, cudaGetLastError());
+    DR_CUDA(ctx, cudaEventRecord(ctx->ev_last, st));
+    ctx->last_stream = st;
+    ctx->have_last = true;
     return DRICE_OK;
 }
 

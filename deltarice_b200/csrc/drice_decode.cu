@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const Par
     const uint32_t nbelow = (lut_s - dsm_s) / kRingBytes;   // rings that fit below the table
     const uint32_t nabove = nwarps > nbelow ? nwarps - nbelow : 0u;
     if (lut_s + kLutBytes + nabove * kRingBytes > dsm_s + p.smem_bytes) {     // launcher and kernel disagree on the layout
-        if (threadIdx.x == 0) atomicOr(p.status, kErrStream);
+        if (threadIdx.x == 0) atomicOr(p.status, kErrInternal);
         return;
     }
     const uint32_t ring_warp_s = (uint32_t)warp < nbelow ? dsm_s + (uint32_t)warp * kRingBytes

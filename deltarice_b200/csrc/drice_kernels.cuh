@@ -23,6 +23,7 @@ constexpr int      kEncTileMaxL      = 8192; // longest wave the warp-per-wave k
 constexpr uint32_t kErrCapacity = 1u;   // output capacity exceeded
 constexpr uint32_t kErrStream   = 2u;   // malformed stream (bad counts / unary run > 8)
 constexpr uint32_t kErrTotal    = 4u;   // chunk's own sample count != expected
+constexpr uint32_t kErrInternal = 8u;   // launcher and kernel disagree (shared-memory layout): a bug here, not a bad stream
 
 struct EncodeParams {
     const int16_t  *raw;

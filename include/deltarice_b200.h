@@ -82,7 +82,10 @@ DRICE_API size_t drice_chunk_bound_bytes(size_t nsamples, int64_t L);
 DRICE_API size_t drice_batch_bound_bytes(const uint64_t *chunk_sample_off, size_t nchunks, int64_t L);
 
 /* Context: one CUDA device, its streams, scratch and pinned staging.  `device` < 0 uses the
- * current device.  Not thread-safe per context; use one context per host thread. */
+ * current device.  Not thread-safe per context; use one context per host thread.  The device
+ * scratch (tickets, look-back words, wave tables) is one set per context: calls may be enqueued on
+ * different streams, a call on another stream than the previous one is ordered behind that call's
+ * last kernel (so two contexts, not two streams, are what runs an encode next to a decode). */
 DRICE_API int  drice_create(drice_ctx **ctx, int device);
 DRICE_API void drice_destroy(drice_ctx *ctx);
 DRICE_API const char *drice_last_error(const drice_ctx *ctx);   /* ctx may be NULL: creation errors */

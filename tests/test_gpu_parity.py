@@ -332,6 +332,45 @@ def test_long_wave_errors(codec, oracle):
     assert np.array_equal(codec.decode_host(s.view(np.uint8), None, None, 8, 40000), x)
 
 
+def test_calls_on_alternating_streams(codec, oracle):
+    """One context, calls enqueued on two different streams back to back with no synchronisation in
+    between: the context's scratch is shared, so a call must be ordered behind the previous call's
+    last kernel (include/deltarice_b200.h).  Results stay bit-exact."""
+    import torch
+    from deltarice_b200.synth import nab_like
+    import deltarice_b200 as d
+    L, M, wpc = 3500, 4, 200
+    xs = [torch.from_numpy(nab_like(4000, L, seed=s).ravel()).cuda() for s in (1, 2)]
+    off = d.chunk_offsets(wpc * L, xs[0].numel())
+    outs = [torch.empty(codec.bound_bytes(off, L), dtype=torch.uint8, device="cuda") for _ in xs]
+    boffs = [torch.zeros(len(off), dtype=torch.int64, device="cuda") for _ in xs]
+    st = [torch.zeros(2, dtype=torch.int32, device="cuda") for _ in range(4)]
+    ys = [torch.empty_like(x) for x in xs]
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for rep in range(5):
+        with torch.cuda.stream(sa):
+            codec.encode_device_async(xs[0], off, M, L, outs[0], boffs[0], st[0])
+        with torch.cuda.stream(sb):
+            codec.encode_device_async(xs[1], off, M, L, outs[1], boffs[1], st[1])
+    torch.cuda.synchronize()
+    hb = [b.cpu().numpy().astype(np.uint64) for b in boffs]
+    for rep in range(5):
+        with torch.cuda.stream(sa):
+            codec.decode_device_async(outs[0][:int(hb[0][-1])], hb[0], off, M, L, ys[0], st[2])
+        with torch.cuda.stream(sb):
+            codec.decode_device_async(outs[1][:int(hb[1][-1])], hb[1], off, M, L, ys[1], st[3])
+    torch.cuda.synchronize()
+    assert all(int(s[0]) == 0 for s in st)
+    for i in range(2):
+        x = xs[i].cpu().numpy()
+        assert torch.equal(ys[i], xs[i])
+        for c in (0, len(off) - 2):
+            want = oracle.encode_chunk(x[int(off[c]):int(off[c + 1])], M, L)
+            got = outs[i][int(hb[i][c]):int(hb[i][c + 1])].cpu().numpy().view(np.uint32)
+            assert np.array_equal(got, want)
+
+
 def test_full_size_c2_roundtrip_and_sampled_parity(codec, oracle):
     """BASELINE config C2 at full size (153 391 Nab-like waves of 3500, M=4, ~1 GB): device
     round trip decode(encode(x)) == x, compression ratio, and byte parity with the oracle on
