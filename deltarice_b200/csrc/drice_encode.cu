@@ -313,6 +313,7 @@ __device__ __forceinline__ void encode_round(RawWords &cur, uint32_t nvalid, boo
     // word holding the sample before this lane's first one in its HIGH half
     uint32_t pw = __shfl_up_sync(0xffffffffu, w[7], 1);
     if (lane == 0) pw = st.prev_last;
+    if (!kFull && nvalid == 0) pw = 0;                   // lanes past the wave's end code nothing: no escape at the boundary
     st.prev_last = __shfl_sync(0xffffffffu, w[7], 31);
 
     // ---- delta + zig-zag on packed halves: D = per-half (x[j] - x[j-1]);  U = (D + D) ^ sign(D)
@@ -613,6 +614,7 @@ __device__ __forceinline__ void encode_round_lut(uint32_t (&w)[NW8], uint32_t nv
     }
     uint32_t pw = __shfl_up_sync(0xffffffffu, w[NW8 - 1], 1);
     if (lane == 0) pw = st.prev_last;
+    if (!kFull && nvalid == 0) pw = 0;                   // lanes past the wave's end code nothing: their (zero) words must not flag an escape at the boundary
     st.prev_last = __shfl_sync(0xffffffffu, w[NW8 - 1], 31);
 
     // ---- one lookup per pair ------------------------------------------------------------------
@@ -724,38 +726,38 @@ __device__ __forceinline__ void encode_round_lut(uint32_t (&w)[NW8], uint32_t nv
 // then at most 2 * NW8 / 16 generic rounds of 512 (the wave's last lane must close the final word in one).
 template <int K, int NW8, bool kDirect, bool kDelta>
 __device__ __forceinline__ uint32_t encode_wave_lut(const int16_t *wave, uint32_t n, const int16_t *raw_hi, int lane,
-                                                    uint32_t *dst, uint32_t cap, bool *overflow, uint32_t tab)
-{
+                                                    uint32_t *dst, uint32_t cap, bool *overflow, uint32_t tab,
+                                                    uint32_t (&w)[NW8], bool preloaded)
+{   // preloaded (warp uniform): w holds the first full round's words already (requested before the previous
+    // wave's copy-out, see the tile kernel)
+    static_assert(NW8 == 8, "one generic round of 512 samples closes the wave");
     constexpr uint32_t kBig = 64u * NW8;                 // samples per full round
     const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(wave) & 15u) >> 1);
-    const uint32_t nbig = n ? (n - 1u) / kBig : 0u;      // the rest (1 .. kBig samples) goes to the generic rounds
+    const uint32_t nbig = n ? (n - 1u) / kBig : 0u;      // the rest (1 .. kBig samples) goes to the generic round
     SweepState st;
     st.base = 0;
     st.carry_round = 0;
     st.prev_last = 0;
     st.ovf = false;
-    uint32_t done = nbig * kBig;
+    // the generic round's slot of this lane
+    const uint32_t s0 = nbig * kBig + lane * 16u;
+    const int32_t rem = (int32_t)n - (int32_t)s0;
+    const uint32_t nv = rem >= 16 ? 16u : (rem > 0 ? (uint32_t)rem : 0u);
     if (nbig) {
-        uint32_t w[NW8];
         const int16_t *q = wave + lane * (2 * NW8);
-        load_words<NW8>(w, q, mis);
+        if (!preloaded) load_words<NW8>(w, q, mis);
         for (uint32_t r = 0; r < nbig; ++r) {
             q += kBig;
+            // the next round's words (the last full round: the generic round's) fly while this one is packed
             encode_round_lut<K, NW8, kDirect, true, kDelta>(w, 2u * NW8, false, lane, dst, cap, st, tab, [&] {
                 if (r + 1 < nbig) load_words<NW8>(w, q, mis);
+                else load_words_tail<NW8>(w, wave + s0, mis, nv, raw_hi);
             });
         }
+    } else {
+        load_words_tail<NW8>(w, wave + s0, mis, nv, raw_hi);
     }
-    // generic rounds of 512 samples (16 per lane)
-    do {
-        const uint32_t s0 = done + lane * 16u;
-        const int32_t rem = (int32_t)n - (int32_t)s0;
-        const uint32_t nv = rem >= 16 ? 16u : (rem > 0 ? (uint32_t)rem : 0u);
-        uint32_t w8[8];
-        load_words_tail<8>(w8, wave + s0, mis, nv, raw_hi);
-        encode_round_lut<K, 8, kDirect, false, kDelta>(w8, nv, nv > 0 && s0 + 16u >= n, lane, dst, cap, st, tab, [] {});
-        done += 512u;
-    } while (done < n);
+    encode_round_lut<K, NW8, kDirect, false, kDelta>(w, nv, nv > 0 && s0 + 16u >= n, lane, dst, cap, st, tab, [] {});
     __syncwarp();
     *overflow = st.ovf;
     return st.base;
@@ -766,7 +768,8 @@ __device__ __noinline__ void encode_wave_lut_in_place(const int16_t *wave, uint3
                                                       uint32_t *dst, uint32_t cap, uint32_t tab)
 {
     bool dummy;
-    encode_wave_lut<K, NW8, true, kDelta>(wave, n, raw_hi, lane, dst, cap, &dummy, tab);
+    uint32_t w[NW8];
+    encode_wave_lut<K, NW8, true, kDelta>(wave, n, raw_hi, lane, dst, cap, &dummy, tab, w, false);
 }
 
 // ---- tile kernel ----------------------------------------------------------------------------
@@ -792,7 +795,8 @@ constexpr int kRing = 3;
 template <int LUT> struct LutVariant { static constexpr int NW8 = 8; };
 template <int K, bool kDirect, bool kDelta, int LUT>
 __device__ __forceinline__ uint32_t encode_wave_any(const int16_t *wave, uint32_t n, const int16_t *raw_hi, int lane,
-                                                    uint32_t *dst, uint32_t cap, bool *overflow, uint32_t tab)
+                                                    uint32_t *dst, uint32_t cap, bool *overflow, uint32_t tab,
+                                                    uint32_t (&w)[8], bool preloaded)
 {
     if constexpr (LUT == 0) {
         return encode_wave<K, kDirect, kDelta>(wave, n, raw_hi, lane, dst, cap, overflow);
@@ -800,7 +804,41 @@ __device__ __forceinline__ uint32_t encode_wave_any(const int16_t *wave, uint32_
         encode_wave_lut_in_place<K, LutVariant<LUT>::NW8, kDelta>(wave, n, raw_hi, lane, dst, cap, tab);
         return 0;
     } else {
-        return encode_wave_lut<K, LutVariant<LUT>::NW8, false, kDelta>(wave, n, raw_hi, lane, dst, cap, overflow, tab);
+        return encode_wave_lut<K, LutVariant<LUT>::NW8, false, kDelta>(wave, n, raw_hi, lane, dst, cap, overflow, tab, w, preloaded);
+    }
+}
+// A worker's wave, kept in shared memory between the iterations of the tile kernel (set up one iteration
+// ahead, encoded, copied out one iteration later): registers are what limits the kernel's occupancy.
+struct WaveSlot {
+    uint64_t begin;         // first sample of the wave in raw
+    uint32_t n;             // samples
+    uint32_t chunk;
+    uint32_t first;         // 1 if first wave of its chunk
+    uint32_t chunk_total;
+    uint32_t nwords;        // record words (after encoding)
+    uint32_t flags;         // bit 0: there is a wave, bit 1: it outgrew its staging
+};
+// Geometry of the wave a worker takes from `tile`; for the table front-end the first full round's words are
+// requested here (waves of more than one round).
+template <int NW, int LUT>
+__device__ __forceinline__ void setup_wave(const EncodeParams &p, uint32_t tile, uint32_t ntiles, int warp, int lane,
+                                           WaveSlot *slot, uint32_t (&w)[8], bool &preloaded)
+{
+    preloaded = false;
+    const uint32_t g = tile * NW + warp;
+    if (tile >= ntiles || g >= p.nwaves) {
+        if (lane == 0) slot->flags = 0;
+        return;
+    }
+    const WaveGeom wg = locate_wave(p, g);
+    if (lane == 0) {
+        slot->begin = wg.begin; slot->n = wg.n; slot->chunk = wg.chunk; slot->first = wg.first;
+        slot->chunk_total = wg.chunk_total; slot->nwords = 0; slot->flags = 1;
+    }
+    if (LUT != 0 && wg.chunk_total && wg.n > 512u) {
+        const int16_t *wave = p.raw + wg.begin;
+        load_words<8>(w, wave + lane * 16, (uint32_t)((reinterpret_cast<uintptr_t>(wave) & 15u) >> 1));
+        preloaded = true;
     }
 }
 template <int K, int LUT>
@@ -817,11 +855,12 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
     __shared__ uint32_t s_total[kRing];
     __shared__ uint64_t s_off[kRing];                    // tile's exclusive word offset
     __shared__ volatile uint32_t s_flag[kRing];          // = it + 1 once s_off is valid
+    __shared__ WaveSlot s_wave[kRing][NW];               // the workers' waves: next / current / previous
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool control = warp == NW;
 
     if (threadIdx.x < kRing) { s_flag[threadIdx.x] = 0; s_cnt[threadIdx.x] = 0; }
-    if (threadIdx.x == 0) s_tile[0] = atomicAdd(p.ticket, 1u);
+    if (threadIdx.x == 0) { s_tile[0] = atomicAdd(p.ticket, 1u); s_tile[1] = atomicAdd(p.ticket, 1u); }
     uint32_t tab = 0;                                    // shared address of the pair table (behind the staging)
     if constexpr (LUT != 0) {
         uint32_t *const tabp = smem + (size_t)(2 * NW) * stage_words;
@@ -852,36 +891,37 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
     }
 
     // ---- workers ---------------------------------------------------------------------------
+    // Tickets are taken ONE tile ahead (s_tile[(it + 1) % kRing] is known during iteration it), so a worker
+    // sets up its next wave - geometry and, for the table front-end, the first round's words - before it
+    // copies out the previous one: the loads fly during the copy-out and the tile barrier.
     uint32_t *const stage0 = smem + (size_t)(2 * warp) * stage_words;   // two staging buffers per warp
     const int16_t *const raw_hi = p.raw + p.raw_samples;
-    WaveGeom wg_prev;
-    uint32_t nwords_prev = 0;
-    bool have_prev = false, ovf_prev = false;
-    wg_prev.g = 0xffffffffu;
     uint32_t largest = 0;                                // largest record of this warp (sizes the next batch's staging)
+    uint32_t w0[8];                                      // first round of the wave set up ahead
+    bool pre = false;
+    setup_wave<NW, LUT>(p, s_tile[0], ntiles, warp, lane, &s_wave[0][warp], w0, pre);
+    __syncwarp();
     for (uint32_t it = 0;; ++it) {
         const int par = it & 1, slot = it % kRing;
         const uint32_t tile = s_tile[slot];
         const bool live = tile < ntiles;
         uint32_t next_ticket = 0;
-        WaveGeom wg;
-        uint32_t nwords = 0;
-        bool have = false, ovf = false;
+        bool pre_next = false;
         if (live) {
-            const uint32_t g = tile * NW + warp;
             uint32_t mine = 0;
-            if (g < p.nwaves) {
-                have = true;
-                wg = locate_wave(p, g);
-                if (wg.chunk_total) {
-                    nwords = (encode_wave_any<K, false, kDelta, LUT>(p.raw + wg.begin, wg.n, raw_hi, lane, stage0 + par * stage_words,
-                                                             stage_words, &ovf, tab) + 31u) >> 5;
+            WaveSlot *const ws = &s_wave[slot][warp];
+            if (ws->flags) {
+                if (ws->chunk_total) {
+                    bool ovf = false;
+                    const uint32_t nwords = (encode_wave_any<K, false, kDelta, LUT>(p.raw + ws->begin, ws->n, raw_hi, lane, stage0 + par * stage_words,
+                                                                            stage_words, &ovf, tab, w0, pre) + 31u) >> 5;
                     mine = nwords + 1u;
                     largest = nwords > largest ? nwords : largest;
+                    if (lane == 0) { ws->nwords = nwords; ws->flags = ovf ? 3u : 1u; }
                 }
-                mine += wg.first;                            // empty chunk: header only
+                mine += ws->first;                           // empty chunk: header only
             }
-            // next tile: taken as late as possible so that tiles start in ticket order; the
+            // the tile after the next: taken as late as possible so that tiles start in ticket order; the
             // atomic's latency hides behind the copy-out below
             if (threadIdx.x == 0) next_ticket = atomicAdd(p.ticket, 1u);
             bool last = false;
@@ -903,45 +943,47 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
             }
             if (__shfl_sync(0xffffffffu, last, 0))           // wakes the control warp
                 asm volatile("bar.arrive %0, 64;" ::"r"(2 + slot) : "memory");
+            setup_wave<NW, LUT>(p, s_tile[(it + 1) % kRing], ntiles, warp, lane, &s_wave[(it + 1) % kRing][warp], w0, pre_next);
         } else if (warp == 0) {
             __threadfence_block();
             asm volatile("bar.arrive %0, 64;" ::"r"(2 + slot) : "memory");   // lets the control warp see the end
         }
         // ---- copy out the wave of the previous iteration ------------------------------------
-        if (have_prev) {
-            const int ps = (it + kRing - 1) % kRing;
+        const int ps = (it + kRing - 1) % kRing;
+        const WaveSlot *const wp = &s_wave[ps][warp];
+        if (it > 0 && wp->flags) {
             while (s_flag[ps] != it) __nanosleep(40);        // tile offset: normally there long ago
             __threadfence_block();
             const uint32_t v = lane < NW ? s_mine[ps][lane] : 0u;
             const uint32_t loff = __reduce_add_sync(0xffffffffu, lane < warp ? v : 0u);
             const uint64_t off = s_off[ps] + loff;
-            const uint32_t rec_words = wg_prev.chunk_total ? nwords_prev + 1u : 0u;
-            const bool fits = off + rec_words + wg_prev.first <= p.out_cap_words;
-            if (lane == 0 && wg_prev.first) p.chunk_byte_off[wg_prev.chunk] = off * 4;
+            const uint32_t nwords_prev = wp->nwords, first_prev = wp->first, total_prev = wp->chunk_total;
+            const uint32_t rec_words = total_prev ? nwords_prev + 1u : 0u;
+            const bool fits = off + rec_words + first_prev <= p.out_cap_words;
+            if (lane == 0 && first_prev) p.chunk_byte_off[wp->chunk] = off * 4;
             if (fits) {
-                uint32_t *rec = p.out + off + wg_prev.first;
+                uint32_t *rec = p.out + off + first_prev;
                 if (lane == 0) {
-                    if (wg_prev.first) p.out[off] = wg_prev.chunk_total;
+                    if (first_prev) p.out[off] = total_prev;
                     if (rec_words) rec[0] = nwords_prev;
                 }
                 if (rec_words) {
-                    if (!ovf_prev) {
+                    if (!(wp->flags & 2u)) {
                         const uint32_t *src = stage0 + (par ^ 1) * stage_words;
                         for (uint32_t i = lane; i < nwords_prev; i += 32) rec[1 + i] = src[i];
                     } else {                                 // larger than the staging: pack in place
                         bool dummy;
-                        encode_wave_any<K, true, kDelta, LUT>(p.raw + wg_prev.begin, wg_prev.n, raw_hi, lane, rec + 1, nwords_prev, &dummy, tab);
+                        uint32_t wd[8];
+                        encode_wave_any<K, true, kDelta, LUT>(p.raw + wp->begin, wp->n, raw_hi, lane, rec + 1, nwords_prev, &dummy, tab, wd, false);
                     }
                 }
             }
             __syncwarp();
         }
         if (!live) break;
-        if (threadIdx.x == 0) s_tile[(it + 1) % kRing] = next_ticket;
-        wg_prev = wg;
-        nwords_prev = nwords;
-        have_prev = have;
-        ovf_prev = ovf;
+        // (slot (it + 2) % kRing was the previous tile's: warp 0 has seen the control warp finish with it above)
+        if (threadIdx.x == 0) s_tile[(it + 2) % kRing] = next_ticket;
+        pre = pre_next;
         // workers only (the control warp runs on its own clock)
         asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
     }
@@ -1229,7 +1271,7 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
     if (want < 64u) want = 64u;
     // room of a geometry: (227 KB - 1 KB reserved per CTA) / CTAs - static shared memory - table
     auto room_words = [&](TileGeom g) -> uint32_t {
-        const size_t per_cta = (size_t)(227 * 1024) / g.ctas - 1024 - 256 - table;
+        const size_t per_cta = (size_t)(227 * 1024) / g.ctas - 1024 - (128 + 108 * (size_t)g.workers) - table;   // (static: ring + wave slots)
         return (uint32_t)(per_cta / ((size_t)g.workers * 8)) & ~3u;
     };
     const TileGeom order[] = {{12, 2}, {24, 1}, {8, 2}, {8, 1}};
@@ -1255,7 +1297,9 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
         const int nthreads = (nworkers + 1) * 32;
         const uint32_t ntiles = (p.nwaves + nworkers - 1) / nworkers;
         if (attr_set.first()) {
-            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+            cudaFuncAttributes fa;                              // (static + dynamic <= 227 KB)
+            cudaFuncGetAttributes(&fa, kernel);
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes);
             cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         }
         int occ = 0;
