@@ -163,12 +163,16 @@ __device__ __forceinline__ uint64_t mul_wide(uint32_t a, uint32_t b)
 template <bool kGuard>
 struct Packer {
     uint32_t lo, n;
-    uint32_t *ptr;
-    uint32_t *end;      // kGuard: nothing is stored at or past `end` (packing straight into HBM)
+    uint32_t *ptr, *first;
+    uint32_t *end;      // nothing is stored at or past `end` (packing straight into HBM)
 
+    __device__ __forceinline__ void init(uint32_t *first_word, uint32_t b0, uint32_t *end_)
+    {
+        n = b0 & 31u; ptr = first = first_word; end = end_; lo = 0;
+    }
     __device__ __forceinline__ void store(uint32_t *q, uint32_t v) const
     {
-        if (!kGuard || q < end) *q = v;
+        if (q < end) *q = v;
     }
     // append one code of len <= 31 bits (value < 2^len)
     __device__ __forceinline__ void put(uint32_t v, uint32_t len)
@@ -181,6 +185,44 @@ struct Packer {
             store(ptr++, __funnelshift_r(alo, (uint32_t)(a >> 32), n));
         }
         lo = alo;
+    }
+    __device__ __forceinline__ uint32_t pending() const { return n; }
+    __device__ __forceinline__ bool flushed() const { return ptr != first; }      // wrote its first word itself
+    __device__ __forceinline__ void store_tail(uint32_t v) const { store(ptr, v); }
+};
+// Packing into the warp's staging in shared memory: `pos` is the lane's running bit position (never
+// wrapped: the funnel shift takes it modulo 32, and a word is complete when bit 5 of the position flips),
+// the emit is four predicated instructions written in PTX so that the pointer advances in place.
+template <>
+struct Packer<false> {
+    uint32_t lo, pos;
+    uint32_t ptr, first;        // shared-memory addresses
+
+    __device__ __forceinline__ void init(uint32_t *first_word, uint32_t b0, uint32_t *)
+    {
+        pos = b0 & 31u; ptr = first = (uint32_t)__cvta_generic_to_shared(first_word); lo = 0;
+    }
+    __device__ __forceinline__ void put(uint32_t v, uint32_t len)
+    {
+        const uint64_t a = mul_wide(lo, pow2(len));
+        const uint32_t alo = (uint32_t)a | v, ahi = (uint32_t)(a >> 32);
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 t, x;\n\t"
+                     "add.u32 t, %1, %4;\n\t"
+                     "xor.b32 x, t, %1;\n\t"
+                     "and.b32 x, x, 32;\n\t"
+                     "setp.ne.u32 p, x, 0;\n\t"
+                     "mov.u32 %1, t;\n\t"
+                     "@p shf.r.wrap.b32 x, %2, %3, t;\n\t"
+                     "@p st.shared.u32 [%0], x;\n\t"
+                     "@p add.u32 %0, %0, 4;\n\t}"
+                     : "+r"(ptr), "+r"(pos) : "r"(alo), "r"(ahi), "r"(len) : "memory");
+        lo = alo;
+    }
+    __device__ __forceinline__ uint32_t pending() const { return pos & 31u; }
+    __device__ __forceinline__ bool flushed() const { return ptr != first; }
+    __device__ __forceinline__ void store_tail(uint32_t v) const
+    {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(ptr), "r"(v) : "memory");
     }
 };
 
@@ -394,11 +436,8 @@ __device__ __forceinline__ void encode_round(RawWords &cur, uint32_t nvalid, boo
 
     // ---- pack ----------------------------------------------------------------------------------
     Packer<kDirect> pk;
-    pk.n = b0 & 31u;
     uint32_t *const first = dst + (b0 >> 5);
-    pk.ptr = first;
-    pk.end = dst + cap;
-    pk.lo = 0;
+    pk.init(first, b0, dst + cap);
     const bool packs = kFull || nvalid > 0;
     if (packs) {
         if (kPairs) {
@@ -428,9 +467,9 @@ __device__ __forceinline__ void encode_round(RawWords &cur, uint32_t nvalid, boo
     // ---- stitch the lanes: the bits a lane left pending belong to the first word the next
     // lane wrote (or still holds) --------------------------------------------------------------
     uint32_t frag;                                       // pending bits, left aligned
-    asm("shl.b32 %0, %1, %2;" : "=r"(frag) : "r"(pk.lo), "r"(32u - pk.n));   // n == 0 -> 0
+    asm("shl.b32 %0, %1, %2;" : "=r"(frag) : "r"(pk.lo), "r"(32u - pk.pending()));   // nothing pending -> 0
     if (!packs) frag = 0;
-    const bool flushed = pk.ptr != first;                // wrote its first word itself
+    const bool flushed = pk.flushed();                   // wrote its first word itself
     constexpr int kStitch = (K == 0) ? 2 : 1;            // 1-bit codes: a lane may hold < 32 bits
 #pragma unroll
     for (int e = 0; e < kStitch; ++e) {
@@ -445,7 +484,7 @@ __device__ __forceinline__ void encode_round(RawWords &cur, uint32_t nvalid, boo
     // the wave's last lane owns the final partial word; bits past the wave's end (padding codes
     // of a short slot) are cleared so the word is zero padded (:237-241)
     if (!kFull && last_lane && packs) {
-        if (pk.n) pk.store(pk.ptr, frag);
+        if (pk.pending()) pk.store_tail(frag);
         if (st.base & 31u) dst[st.base >> 5] &= 0xFFFFFFFFu << (32u - (st.base & 31u));
     }
 }
@@ -682,11 +721,8 @@ __device__ __forceinline__ void encode_round_lut(uint32_t (&w)[NW8], uint32_t nv
 
     // ---- pack ----------------------------------------------------------------------------------
     Packer<kDirect> pk;
-    pk.n = b0 & 31u;
     uint32_t *const first = dst + (b0 >> 5);
-    pk.ptr = first;
-    pk.end = dst + cap;
-    pk.lo = 0;
+    pk.init(first, b0, dst + cap);
     const bool packs = kFull || nvalid > 0;
     if (packs) {
         if (!any_flag) {
@@ -703,7 +739,7 @@ __device__ __forceinline__ void encode_round_lut(uint32_t (&w)[NW8], uint32_t nv
     }
     // ---- stitch the lanes (see encode_round) ---------------------------------------------------
     uint32_t frag;
-    asm("shl.b32 %0, %1, %2;" : "=r"(frag) : "r"(pk.lo), "r"(32u - pk.n));
+    asm("shl.b32 %0, %1, %2;" : "=r"(frag) : "r"(pk.lo), "r"(32u - pk.pending()));
     if (!packs) frag = 0;
     uint32_t from_prev = __shfl_up_sync(0xffffffffu, frag, 1);
     if (lane == 0) from_prev = st.carry_round;
@@ -711,13 +747,13 @@ __device__ __forceinline__ void encode_round_lut(uint32_t (&w)[NW8], uint32_t nv
         // a full lane holds >= 16 (K + 1) >= 32 bits: its first word is in the staging already
         *first |= from_prev;
     } else if (packs) {
-        const bool flushed = pk.ptr != first;
-        if (flushed) { if (from_prev) { if (!kDirect || first < pk.end) *first |= from_prev; } }
+        const bool flushed = pk.flushed();
+        if (flushed) { if (from_prev) { if (!kDirect || first < dst + cap) *first |= from_prev; } }
         else frag |= from_prev;
     }
     st.carry_round = __shfl_sync(0xffffffffu, frag, 31);
     if (!kFull && last_lane && packs) {
-        if (pk.n) pk.store(pk.ptr, frag);
+        if (pk.pending()) pk.store_tail(frag);
         if (st.base & 31u) dst[st.base >> 5] &= 0xFFFFFFFFu << (32u - (st.base & 31u));
     }
 }
@@ -860,7 +896,9 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
     const bool control = warp == NW;
 
     if (threadIdx.x < kRing) { s_flag[threadIdx.x] = 0; s_cnt[threadIdx.x] = 0; }
-    if (threadIdx.x == 0) { s_tile[0] = atomicAdd(p.ticket, 1u); s_tile[1] = atomicAdd(p.ticket, 1u); }
+    // the first two tiles of a CTA are fixed (all CTAs are resident and run iteration 0 together, so tiles
+    // still start in index order); later ones come from the ticket counter, one iteration ahead
+    if (threadIdx.x == 0) { s_tile[0] = blockIdx.x; s_tile[1] = gridDim.x + blockIdx.x; }
     uint32_t tab = 0;                                    // shared address of the pair table (behind the staging)
     if constexpr (LUT != 0) {
         uint32_t *const tabp = smem + (size_t)(2 * NW) * stage_words;
@@ -923,7 +961,7 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
             }
             // the tile after the next: taken as late as possible so that tiles start in ticket order; the
             // atomic's latency hides behind the copy-out below
-            if (threadIdx.x == 0) next_ticket = atomicAdd(p.ticket, 1u);
+            if (threadIdx.x == 0) next_ticket = 2u * gridDim.x + atomicAdd(p.ticket, 1u);
             bool last = false;
             if (lane == 0) {
                 s_mine[slot][warp] = mine;
@@ -970,7 +1008,12 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
                 if (rec_words) {
                     if (!(wp->flags & 2u)) {
                         const uint32_t *src = stage0 + (par ^ 1) * stage_words;
-                        for (uint32_t i = lane; i < nwords_prev; i += 32) rec[1 + i] = src[i];
+                        uint32_t i = lane;
+                        for (; i + 96u < nwords_prev; i += 128u) {          // four independent words per lane and trip
+                            const uint32_t a = src[i], b = src[i + 32], c = src[i + 64], d = src[i + 96];
+                            rec[1 + i] = a; rec[33 + i] = b; rec[65 + i] = c; rec[97 + i] = d;
+                        }
+                        for (; i < nwords_prev; i += 32u) rec[1 + i] = src[i];
                     } else {                                 // larger than the staging: pack in place
                         bool dummy;
                         uint32_t wd[8];
@@ -1274,15 +1317,23 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
         const size_t per_cta = (size_t)(227 * 1024) / g.ctas - 1024 - (128 + 108 * (size_t)g.workers) - table;   // (static: ring + wave slots)
         return (uint32_t)(per_cta / ((size_t)g.workers * 8)) & ~3u;
     };
-    const TileGeom order[] = {{12, 2}, {24, 1}, {8, 2}, {8, 1}};
+    const TileGeom order[] = {{12, 2}, {13, 2}, {24, 1}, {8, 2}, {8, 1}};
     TileGeom geom = order[3];
     bool found = false;
     for (const TileGeom g : order) {
-        if ((!lut || !md.delta) && g.workers == 24) continue;          // (only the table kernel is built for 24 workers)
+        if ((!lut || !md.delta) && (g.workers == 24 || g.workers == 13)) continue;   // (only the table kernel is built for 13 / 24 workers)
+        if (g.workers == 13 && workers_env != 13) continue;          // (13 is chosen below)
         if (workers_env && g.workers != workers_env) continue;
         if (room_words(g) >= want || (!md.words_hint && stage_env <= 0 && g.workers == 12)) { geom = g; found = true; break; }
     }
     if (!found && workers_env) for (const TileGeom g : order) if (g.workers == workers_env) { geom = g; break; }
+    // 12 or 13 workers: whichever leaves the smaller last round of tiles (cost = rounds of tiles x workers; C2:
+    // 44 x 12 against 40 x 13, measured 0.550 against 0.543 ms)
+    if (lut && geom.workers == 12 && geom.ctas == 2 && !workers_env && room_words({13, 2}) >= want) {
+        const uint64_t ctas = 2ull * (uint64_t)g_num_sms;
+        const uint64_t c12 = ((p.nwaves + ctas * 12 - 1) / (ctas * 12)) * 12, c13 = ((p.nwaves + ctas * 13 - 1) / (ctas * 13)) * 13;
+        if (c13 < c12) geom.workers = 13;
+    }
     uint32_t stage = room_words(geom) < want ? room_words(geom) : want;
     if (!md.words_hint && stage_env <= 0) stage = room_words(geom) < worst ? room_words(geom) : worst;   // no hint: all the room
     stage = (stage + 3u) & ~3u;
@@ -1309,10 +1360,11 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
         if (grid > ntiles) grid = ntiles;
         kernel<<<grid, nthreads, smem, st>>>(p, stage, ntiles, md.max_words);
     };
-    static DeviceOnce a12, a8, a8n, t12, t24, t8;                // per K (this function is a template)
+    static DeviceOnce a12, a8, a8n, t12, t13, t24, t8;                // per K (this function is a template)
     if constexpr (LutConst<K>::kOk) {
         if (lut) {
             if (geom.workers == 12) launch(encode_tile_kernel<K, 2, true, 12, 1>, t12, 12);
+            else if (geom.workers == 13) launch(encode_tile_kernel<K, 2, true, 13, 1>, t13, 13);
             else if (geom.workers == 24) launch(encode_tile_kernel<K, 1, true, 24, 1>, t24, 24);
             else launch(encode_tile_kernel<K, 2, true, 8, 1>, t8, 8);
             return 1;
