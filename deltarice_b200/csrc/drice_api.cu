@@ -543,8 +543,11 @@ extern "C" int drice_encode_batch_dev_async(drice_ctx *ctx, const int16_t *d_raw
     if (!d_raw && off[nchunks] > 0) return fail(ctx, DRICE_E_PARAM, "null input");
     // scratch: [ticket u32][pad] | look-back status u64 per tile (at most one per wave): all zeroed
     const size_t zeroed = ((size_t)g.nwaves * 8 + 16 + 15) & ~(size_t)15;
-    if (zeroed > ctx->d_scratch.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
-    DR_CUDA(ctx, ctx->d_scratch.reserve(zeroed));
+    // + the segment tables of the long-wave encoder (few waves of more than 8192 samples; not zeroed)
+    size_t long_bytes = g.nwaves <= 1024 ? encode_long_scratch_bytes(g.nwaves, g.max_wave) : 0;
+    if (long_bytes > ((size_t)64 << 20)) long_bytes = 0;
+    if (zeroed + long_bytes > ctx->d_scratch.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
+    DR_CUDA(ctx, ctx->d_scratch.reserve(zeroed + long_bytes));
     uint64_t *d_soff, *d_unused;
     uint32_t *d_woff;
     rc = upload_tables(ctx, off, nullptr, g.wave_off.data(), nchunks, st, &d_soff, &d_unused, &d_woff,
@@ -578,6 +581,8 @@ extern "C" int drice_encode_batch_dev_async(drice_ctx *ctx, const int16_t *d_raw
     ctx->hint_wave = g.max_wave;
     ctx->hint_k = k;
     md.max_words = ctx->d_hint;
+    md.long_scratch = long_bytes ? (char *)ctx->d_scratch.p + zeroed : nullptr;
+    md.long_scratch_bytes = long_bytes;
     p.raw_samples = off[nchunks];
     p.out = d_out;
     p.out_cap_words = out_cap_bytes / 4;

@@ -1283,6 +1283,248 @@ encode_multi_kernel(const EncodeParams p, const int dmask)
     pack_wave_streaming<K>(wave, wg.n, rec, smem, dmask);
 }
 
+// ======================================================================================
+// long waves in small batches: several CTAs per wave
+// ======================================================================================
+// One CTA per wave (encode_multi_kernel) leaves most SMs idle when a batch has a handful of very long waves
+// - the reference's long-wave configurations (docs/Performance.md:27-47) and its DEFAULT WaveformLength = -1
+// (the whole chunk is one wave).  Here a wave is cut into segments of kLongSegSlots slots (16 samples each,
+// aligned to memory as in slot_codes); work item = (wave, segment):
+//   1. encode_long_size_kernel  - bits of every segment (a sizing sweep);
+//   2. encode_long_scan_kernel  - one CTA: per wave (a warp each) the segments' exclusive bit offsets and the
+//      record's word count, then across the waves the record offsets; writes the chunk / record headers and
+//      the chunk byte offsets, and zeroes the words two segments share;
+//   3. encode_long_pack_kernel  - packs every segment at its bit offset: whole words with plain stores, the
+//      first and last (shared) word with atomicOr.
+constexpr uint32_t kLongSegTiles = 2;                                  // tiles of kEncMaxThreads slots per segment
+constexpr uint32_t kLongSegSlots = kLongSegTiles * kEncMaxThreads;     // 16384 samples
+
+struct LongParams {
+    EncodeParams p;
+    uint64_t *seg_bits;      // [nwaves * maxseg]: bits of a segment, then (after the scan) its exclusive bit offset
+    uint64_t *wave_off;      // [nwaves]: word offset of the wave's first output word (chunk header or record header)
+    uint32_t  maxseg;
+    int       dmask;
+};
+
+__device__ __forceinline__ uint32_t long_wave_slots(const int16_t *wave, uint32_t n)
+{
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(wave) & 31u) >> 1);
+    return (uint32_t)(((uint64_t)mis + n + S - 1) / S);
+}
+
+template <int K>
+__global__ void __launch_bounds__(kEncMaxThreads)
+encode_long_size_kernel(const LongParams lp)
+{
+    __shared__ uint64_t s64[kEncMaxThreads / 32];
+    const EncodeParams &p = lp.p;
+    const uint32_t g = blockIdx.y, seg = blockIdx.x;
+    const WaveGeom wg = locate_wave(p, g);
+    const int16_t *wave = p.raw + wg.begin;
+    const uint32_t nslots = long_wave_slots(wave, wg.n);
+    const uint32_t s_lo = seg * kLongSegSlots;
+    if (s_lo >= nslots) return;
+    const uint32_t s_hi = min(nslots, s_lo + kLongSegSlots);
+    const int mis = (int)((reinterpret_cast<uintptr_t>(wave) & 31u) >> 1);
+    uint32_t cv[S];
+    uint64_t bits = 0;
+    for (uint32_t sl = s_lo + threadIdx.x; sl < s_hi; sl += kEncMaxThreads)
+        bits += slot_codes<K>(wave, (int64_t)sl * S - mis, wg.n, cv, lp.dmask);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
+    if ((threadIdx.x & 31) == 0) s64[threadIdx.x >> 5] = bits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t tot = 0;
+        for (int w = 0; w < kEncMaxThreads / 32; ++w) tot += s64[w];
+        lp.seg_bits[(size_t)g * lp.maxseg + seg] = tot;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+encode_long_scan_kernel(const LongParams lp)
+{
+    const EncodeParams &p = lp.p;
+    __shared__ uint64_t s_words[1024];       // output words of each wave (record + chunk header), then their exclusive scan
+    __shared__ uint64_t s_warp[33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // ---- per wave (a warp each): exclusive bit offsets of its segments, record size --------------------
+    for (uint32_t g = warp; g < p.nwaves; g += 32) {
+        const WaveGeom wg = locate_wave(p, g);
+        const uint32_t nslots = long_wave_slots(p.raw + wg.begin, wg.n);
+        const uint32_t nseg = (nslots + kLongSegSlots - 1) / kLongSegSlots;
+        uint64_t *sb = lp.seg_bits + (size_t)g * lp.maxseg;
+        uint64_t run = 0;
+        for (uint32_t s0 = 0; s0 < nseg; s0 += 32) {
+            const uint32_t sg = s0 + lane;
+            const uint64_t v = sg < nseg ? sb[sg] : 0ull;
+            uint64_t inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            if (sg < nseg) sb[sg] = run + inc - v;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) {
+            const uint64_t nwords = (run + 31u) >> 5;
+            // the wave's words: [chunk total] (first wave of a chunk) + [nwords] + words (nothing for an empty chunk)
+            s_words[g] = (wg.chunk_total ? nwords + 1u : 0u) + wg.first;
+            // total bits kept for the pack kernel's end word: slot nseg of the row (maxseg has room for it)
+            sb[nseg] = run;
+        }
+    }
+    __syncthreads();
+    // ---- across the waves: exclusive scan of their words (nwaves <= 1024) -----------------------------
+    {
+        const uint32_t g = threadIdx.x;
+        const uint64_t v = g < p.nwaves ? s_words[g] : 0ull;
+        uint64_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const uint64_t ws = s_warp[lane];
+            uint64_t wi = ws;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t t = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += t;
+            }
+            s_warp[lane] = wi - ws;
+            if (lane == 31) s_warp[32] = wi;
+        }
+        __syncthreads();
+        const uint64_t excl = s_warp[warp] + inc - v;
+        const uint64_t total = s_warp[32];
+        const bool fits = total <= p.out_cap_words;
+        if (threadIdx.x == 0) {
+            if (!fits) atomicOr(p.status, kErrCapacity);
+            p.chunk_byte_off[p.nchunks] = total * 4;
+        }
+        __syncthreads();
+        if (g < p.nwaves) {
+            s_words[g] = excl;
+            lp.wave_off[g] = fits ? excl : ~0ull;                // ~0: nothing is written
+        }
+        __syncthreads();
+        if (!fits) {
+            // offsets are still reported (as the other kernels do); no data is written
+            if (g < p.nwaves) {
+                const WaveGeom wg = locate_wave(p, g);
+                if (wg.first) p.chunk_byte_off[wg.chunk] = excl * 4;
+            }
+            return;
+        }
+    }
+    // ---- headers, and zeroes under every word two segments share (a warp per wave) --------------------
+    for (uint32_t g = warp; g < p.nwaves; g += 32) {
+        const WaveGeom wg = locate_wave(p, g);
+        const uint64_t off = s_words[g];
+        const uint32_t nslots = long_wave_slots(p.raw + wg.begin, wg.n);
+        const uint32_t nseg = (nslots + kLongSegSlots - 1) / kLongSegSlots;
+        const uint64_t *sb = lp.seg_bits + (size_t)g * lp.maxseg;
+        uint32_t *rec = p.out + off + wg.first;
+        if (lane == 0) {
+            if (wg.first) { p.out[off] = wg.chunk_total; p.chunk_byte_off[wg.chunk] = off * 4; }
+            if (wg.chunk_total) rec[0] = (uint32_t)((sb[nseg] + 31u) >> 5);
+        }
+        if (wg.chunk_total) {
+            for (uint32_t sg = lane; sg <= nseg; sg += 32) {     // (entry nseg = the wave's end)
+                const uint64_t b = sb[sg];
+                if (b & 31u) rec[1 + (b >> 5)] = 0u;
+            }
+        }
+    }
+}
+
+// packs the slots [s_lo, s_hi) of one wave; P0 = bit offset of the segment's first bit in the record
+template <int K>
+__device__ __forceinline__ void pack_segment_streaming(const int16_t *wave, uint32_t n, uint32_t *rec, uint32_t *smem, int dmask,
+                                                       uint32_t s_lo, uint32_t s_hi, uint64_t P0)
+{
+    constexpr int NT = kEncMaxThreads;
+    const int tid = threadIdx.x;
+    uint32_t *sbits = smem;                  // NT*13 + 1 (worst case 12.5 words per slot)
+    uint32_t *shead = sbits + NT * 13 + 1;   // NT
+    uint32_t *sboff = shead + NT;            // NT
+    uint32_t *swarp = sboff + NT;            // 33
+    __shared__ uint32_t s_carry;
+    const int mis = (int)((reinterpret_cast<uintptr_t>(wave) & 31u) >> 1);
+    uint32_t cv[S];
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    uint64_t P = P0;                           // bits of the record before the current tile
+    const uint64_t shared_first = (P0 & 31u) ? (P0 >> 5) : ~0ull;   // word shared with the previous segment
+    for (uint32_t t0 = s_lo; t0 < s_hi; t0 += NT) {
+        const uint32_t sl = t0 + tid;
+        uint32_t T = 0;
+        if (sl < s_hi) T = slot_codes<K>(wave, (int64_t)sl * S - mis, n, cv, dmask);
+        else {
+#pragma unroll
+            for (int j = 0; j < S; ++j) cv[j] = 0;
+        }
+        uint32_t total;
+        const uint32_t boff = block_excl_scan(T, swarp, &total);
+        const uint32_t pre = (uint32_t)(P & 31u);          // bits already in word 0 (carry)
+        const uint32_t b0 = pre + boff;
+        bool owner;
+        uint32_t tail, wt;
+        shead[tid] = 0;
+        sboff[tid] = b0;
+        pack_slot(cv, b0, T, sbits, shead, owner, tail, wt);
+        __syncthreads();
+        if (owner) {
+            for (uint32_t j = tid + 1; j < (uint32_t)NT && (sboff[j] >> 5) == wt; ++j) tail |= shead[j];
+            sbits[wt] = tail;
+        }
+        if (tid == 0 && pre) {                 // word 0 was started by the previous tile (or segment)
+            uint32_t c = s_carry;
+            for (uint32_t j = 0; j < (uint32_t)NT && (sboff[j] >> 5) == 0; ++j) c |= shead[j];
+            sbits[0] = c;
+        }
+        __syncthreads();
+        const uint32_t bend = pre + total;
+        const uint32_t full = bend >> 5;
+        const uint64_t w0 = P >> 5;
+        uint32_t *dstw = rec + 1 + w0;
+        for (uint32_t w = tid; w < full; w += NT) {
+            if (w0 + w == shared_first) atomicOr(dstw + w, sbits[w]);
+            else dstw[w] = sbits[w];
+        }
+        if (tid == 0) s_carry = (bend & 31u) ? sbits[full] : 0u;
+        P += total;
+        __syncthreads();
+    }
+    if (tid == 0 && (P & 31u)) atomicOr(rec + 1 + (P >> 5), s_carry);   // shared with the next segment (zeroed by the scan)
+}
+
+template <int K>
+__global__ void __launch_bounds__(kEncMaxThreads)
+encode_long_pack_kernel(const LongParams lp)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const EncodeParams &p = lp.p;
+    const uint32_t g = blockIdx.y, seg = blockIdx.x;
+    const WaveGeom wg = locate_wave(p, g);
+    if (wg.chunk_total == 0) return;
+    const int16_t *wave = p.raw + wg.begin;
+    const uint32_t nslots = long_wave_slots(wave, wg.n);
+    const uint32_t s_lo = seg * kLongSegSlots;
+    if (s_lo >= nslots) return;
+    const uint64_t off = lp.wave_off[g];
+    if (off == ~0ull) return;                                    // does not fit: flagged by the scan
+    uint32_t *rec = p.out + off + wg.first;
+    pack_segment_streaming<K>(wave, wg.n, rec, smem, lp.dmask, s_lo, min(nslots, s_lo + kLongSegSlots),
+                              lp.seg_bits[(size_t)g * lp.maxseg + seg]);
+}
+
 // Launch geometry of the tile kernel.  Shared memory per CTA = two staging buffers of `stage` words per
 // worker warp (+ the pair table); a wave that outgrows its staging is packed a second time straight into
 // its record, so the staging should hold the batch's largest record: it is sized from the largest record
@@ -1299,6 +1541,25 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
     const int g_num_sms = device_sm_count();
     const size_t smem_multi = (size_t)(kEncMaxThreads * 13 + 1 + 2 * kEncMaxThreads + 33 + 3) * sizeof(uint32_t);
     if (max_wave_len > (uint32_t)kEncTileMaxL) {
+        // few long waves: several CTAs per wave (three launches); many: one CTA per wave
+        const uint32_t maxseg = encode_long_maxseg(max_wave_len);
+        if (md.long_scratch && p.nwaves < 4u * (uint32_t)g_num_sms && p.nwaves <= 1024u &&
+            encode_long_scratch_bytes(p.nwaves, max_wave_len) <= md.long_scratch_bytes) {
+            LongParams lp;
+            lp.p = p;
+            lp.seg_bits = (uint64_t *)md.long_scratch;
+            lp.wave_off = lp.seg_bits + (size_t)p.nwaves * maxseg;
+            lp.maxseg = maxseg;
+            lp.dmask = md.delta ? -1 : 0;
+            static DeviceOnce once;
+            if (once.first())
+                cudaFuncSetAttribute(encode_long_pack_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
+            const dim3 grid(maxseg - 1, p.nwaves);               // (the row's last entry is the wave's end, not a segment)
+            encode_long_size_kernel<K><<<grid, kEncMaxThreads, 0, st>>>(lp);
+            encode_long_scan_kernel<<<1, 1024, 0, st>>>(lp);
+            encode_long_pack_kernel<K><<<grid, kEncMaxThreads, smem_multi, st>>>(lp);
+            return 3;
+        }
         encode_multi_kernel<K><<<p.nwaves, kEncMaxThreads, smem_multi, st>>>(p, md.delta ? -1 : 0);
         return 1;
     }
@@ -1418,6 +1679,19 @@ int DRICE_CAT(launch_encode_part, DRICE_PART)(const EncodeParams &p, const Encod
 #endif
 #undef DRICE_CASE
 
+#if DRICE_PART == 0
+// rows of the long-wave encoder's segment table: segments of the longest wave (+ 1 slot of misalignment) + the end entry
+uint32_t encode_long_maxseg(uint32_t max_wave_len)
+{
+    const uint64_t slots = ((uint64_t)max_wave_len + 15u + 15u) / 16u;
+    return (uint32_t)((slots + 1024u - 1u) / 1024u) + 1u;
+}
+size_t encode_long_scratch_bytes(uint32_t nwaves, uint32_t max_wave_len)
+{
+    if (max_wave_len <= (uint32_t)kEncTileMaxL) return 0;
+    return ((size_t)nwaves * encode_long_maxseg(max_wave_len) + nwaves) * sizeof(uint64_t);
+}
+#endif
 #if DRICE_PART == 0
 int launch_encode(const EncodeParams &p, const EncodeMode &m, uint32_t max_wave_len, cudaStream_t st)
 {

@@ -53,6 +53,9 @@ struct EncodeMode {
     // sizes the tile kernel's staging; the launch raises *max_words (device) with its own largest record
     uint32_t        words_hint;
     uint32_t       *max_words;
+    // scratch of the long-wave encoder (encode_long_scratch_bytes; need not be zeroed), or null
+    void           *long_scratch;
+    size_t          long_scratch_bytes;
 };
 
 // generic pre-filter (src/deltaRice.c:64-74 / :91-102), taps by value
@@ -170,6 +173,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 
 // launchers (drice_encode.cu / drice_decode.cu); return launches enqueued
 int launch_encode(const EncodeParams &p, const EncodeMode &m, uint32_t max_wave_len, cudaStream_t st);
+// few waves longer than kEncTileMaxL are encoded by several CTAs per wave: scratch for their segment tables
+uint32_t encode_long_maxseg(uint32_t max_wave_len);
+size_t encode_long_scratch_bytes(uint32_t nwaves, uint32_t max_wave_len);
 int launch_locate(const LocateParams &p, cudaStream_t st);
 // header scan instead of the chase (drice_decode.cu): applicability + scratch size, launcher
 bool locate_scan_applies(uint32_t L, int k, uint64_t max_chunk_words, size_t nchunks, size_t *scratch_bytes);

@@ -300,10 +300,14 @@ def test_errors(codec, oracle):
     (4, 8193, [8193 * 5, 8193 * 2 + 77, 1], 3.0),   # just past the tile kernels' 8192 samples
     (16, 20000, [20000 * 7], 3000.0),               # escape dominated: 25-bit codes, many segments per wave
     (1, 30000, [30000 * 2], 0.7),                   # RiceParameter 1
+    (8, None, [100001, 0, 16385, 1, 9000], 10.0),   # whole-chunk waves of odd sizes (every alignment), an empty chunk, one sample
+    (4, 8200, [8200 * 640], 3.0),                   # MANY long waves: one CTA per wave (encode_multi_kernel), lane parser
+    (2, 16400, [16400 * 3 + 5], 2.0),               # segments that end inside a word, short ragged last wave
 ])
 def test_long_waves(codec, oracle, M, L, sizes, sigma):
-    """Waves longer than 8192 samples in small batches: encode_multi_kernel and parse_long_kernel (several
-    CTAs per wave, chained along the record).  Bit-exact against the oracle, exact round trip."""
+    """Waves longer than 8192 samples: in small batches the encode_long_* kernels (several CTAs per wave: sizing,
+    scan, packing at the segments' bit offsets) and parse_long_kernel (several CTAs per wave, chained along the
+    record); in large ones encode_multi_kernel and the lane parser.  Bit-exact against the oracle, exact round trip."""
     r = np.random.default_rng(77)
     off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
     x = np.clip(np.rint(np.cumsum(r.normal(0, sigma, int(off[-1]))) % 3000 - 1500 + r.normal(0, sigma, int(off[-1]))),
@@ -315,6 +319,37 @@ def test_long_waves(codec, oracle, M, L, sizes, sigma):
     assert np.array_equal(codec.decode_host(got, boff, off, M, L), x)
     # the oracle's stream decodes as well (the parser does not rely on our encoder)
     assert np.array_equal(codec.decode_host(want.view(np.uint8), wboff, off, M, L), x)
+
+
+def test_long_wave_capacity_and_filter(codec, oracle):
+    """The several-CTAs-per-wave encoder: an output buffer that is too small is reported (nothing is written
+    past it), and option tuples whose pre-filter is [1] (no delta) take the same kernels."""
+    import deltarice_b200 as d
+    import torch
+    r = np.random.default_rng(9)
+    x = np.clip(np.rint(np.cumsum(r.normal(0, 5, 50000)) % 2000 - 1000), -32768, 32767).astype(np.int16)
+    off = np.array([0, x.size], dtype=np.uint64)
+    want = oracle.encode_chunk(x, 8, 25000)
+    xd = torch.from_numpy(x).cuda()
+    small = torch.full((want.size * 4 // 2 + 64,), 0xA5, dtype=torch.uint8, device="cuda")
+    boff = torch.zeros(2, dtype=torch.int64, device="cuda")
+    status = torch.zeros(2, dtype=torch.int32, device="cuda")
+    codec.encode_device_async(xd, off, 8, 25000, small[:want.size * 2], boff, status)
+    torch.cuda.synchronize()
+    assert int(status[0]) & 1                                     # DRICE capacity flag
+    assert int(boff[1]) == want.size * 4                          # the needed size is still reported
+    assert bool((small[want.size * 2:] == 0xA5).all())            # nothing past the capacity
+    got, _ = codec.encode_host(x, off, 8, 25000)
+    assert np.array_equal(got.view(np.uint32), want)
+    # filter [1]: the samples are coded as they are
+    f = d.DeltaRice(0)
+    f.set_filter([1])
+    xs = (x // 64).astype(np.int16)
+    wantf = oracle.encode_chunk(xs, 8, 25000, filt=[1])
+    gotf, bo = f.encode_host(xs, off, 8, 25000)
+    assert np.array_equal(gotf.view(np.uint32), wantf)
+    assert np.array_equal(f.decode_host(gotf, bo, off, 8, 25000), xs)
+    f.close()
 
 
 def test_long_wave_errors(codec, oracle):
