@@ -1,2 +1,2 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "long" 2>&1 | tail -15
-timeout 600 python tools/long_waves.py 7 2>&1 | tail -4
+python bench.py --steps 20 --warmup 3 > gpurun_out/r2f_c2.json 2> gpurun_out/r2f_c2.err
+python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/r2f_c2_ref.json 2> gpurun_out/r2f_c2_ref.err
