@@ -14,7 +14,7 @@
 //   * persistent CTAs of NW worker warps + 1 control warp; a tile = NW consecutive waves taken from an
 //     atomic ticket; ONE WARP ENCODES ONE WAVE, 16 samples (8 packed int16x2 words) per lane and round;
 //     the next round's words are loaded between the round's front-end and its packing;
-//   * table front-end (RiceParameter 2, 4, 8; encode_round_lut): t = delta + 4M on packed halves
+//   * table front-end (RiceParameter 2 ... 64; encode_round_lut): t = delta + R (R = min(4M, 32)) on packed halves
 //     (PRMT / LOP3 / 2 x VIADD.16x2), the two (k+3)-bit fields become the offset of the pair's entry
 //     with LOP3 / IMAD / SHF, one LDS returns the pair's code | length << 24 from a skewed table in
 //     shared memory; pairs that hold an escape (a half outside the table) are redone per sample in a
@@ -532,8 +532,8 @@ __device__ __forceinline__ uint32_t encode_wave(const int16_t *wave, uint32_t n,
 // ======================================================================================
 // table front-end: one shared-memory lookup per PAIR of samples
 // ======================================================================================
-// For 1 <= K <= 3 the Rice split of a pair of deltas (src/deltaRice.c:207-222) is a table: when both
-// deltas lie in [-R, R) with R = 4M (quotients < 8, no escape), the pair's code and length are a
+// For 1 <= K <= 6 the Rice split of a pair of deltas (src/deltaRice.c:207-222) is a table: when both
+// deltas lie in [-R, R) with R = min(4M, 32) (quotients < 8, no escape), the pair's code and length are a
 // function of 2(K+3) bits.  The lane forms t = delta + R on packed halves (no zig-zag: the table
 // absorbs it), one LOP3 / IMAD / SHF turn the two (K+3)-bit fields into the entry's offset and one
 // LDS fetches code | length << 24.  Halves outside [0, 2R) flag the pair: it is redone per sample
@@ -542,9 +542,9 @@ __device__ __forceinline__ uint32_t encode_wave(const int16_t *wave, uint32_t n,
 // skew the bank (= lo mod 32) would be the same handful for every lane.
 template <int K>
 struct LutConst {
-    static constexpr bool     kOk   = (K >= 1 && K <= 3);
-    static constexpr uint32_t R     = 4u << K;
-    static constexpr uint32_t IDXB  = K + 3;                                   // bits of one biased delta
+    static constexpr bool     kOk   = (K >= 1 && K <= 6);
+    static constexpr uint32_t IDXB  = (K + 3 < 6) ? K + 3 : 6;                 // bits of one biased delta (table of <= 17.6 KB)
+    static constexpr uint32_t R     = 1u << (IDXB - 1);                        // 4M for K <= 3, 32 (quotients < 64 / 2M) above
     static constexpr uint32_t kSkew = 5;
     static constexpr uint32_t ROW   = (1u << IDXB) + kSkew;
     static constexpr uint32_t LOW   = (2u * R - 1u) * 0x10001u;
@@ -825,7 +825,7 @@ constexpr int kRing = 3;
 // NW worker warps (+ 1 control warp) per CTA: 12 for short waves (two CTAs per SM: measured best,
 // 0.69 vs 0.74 ms for 3 x 8 on C2; 13 and 14 lose to register pressure), 8 when the staging of
 // longer waves needs the room
-// LUT: 0 = arithmetic front-end (encode_round), 1 = table front-end (1 <= K <= 3), 16 samples per lane and round
+// LUT: 0 = arithmetic front-end (encode_round), 1 = table front-end (1 <= K <= 6), 16 samples per lane and round
 // (32 per lane were measured too: twice as slow - registers spill and the unrolled round outgrows the
 // instruction cache)
 template <int LUT> struct LutVariant { static constexpr int NW8 = 8; };
@@ -1566,8 +1566,8 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
     static const int lut_env = [] { const char *v = getenv("DRICE_ENC_LUT"); return v ? atoi(v) : 1; }();
     static const int workers_env = [] { const char *v = getenv("DRICE_ENC_WORKERS"); return v ? atoi(v) : 0; }();
     static const long stage_env = [] { const char *v = getenv("DRICE_ENC_STAGE_WORDS"); return v ? atol(v) : 0l; }();
-    const bool lut = LutConst<K>::kOk && md.delta && lut_env != 0;
-    const size_t table = lut ? lut_table_bytes<K, 1>() : 0;
+    bool lut = LutConst<K>::kOk && md.delta && lut_env != 0;
+    size_t table = lut ? lut_table_bytes<K, 1>() : 0;
     const uint32_t worst = (25u * max_wave_len + 31u) / 32u + 24u;
     uint32_t want = md.words_hint ? md.words_hint + md.words_hint / 16u + 24u : (10u * max_wave_len + 31u) / 32u + 24u;
     if (stage_env > 0) want = (uint32_t)stage_env;
@@ -1578,16 +1578,29 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
         const size_t per_cta = (size_t)(227 * 1024) / g.ctas - 1024 - (128 + 108 * (size_t)g.workers) - table;   // (static: ring + wave slots)
         return (uint32_t)(per_cta / ((size_t)g.workers * 8)) & ~3u;
     };
-    const TileGeom order[] = {{12, 2}, {13, 2}, {24, 1}, {8, 2}, {8, 1}};
-    TileGeom geom = order[3];
-    bool found = false;
-    for (const TileGeom g : order) {
-        if ((!lut || !md.delta) && (g.workers == 24 || g.workers == 13)) continue;   // (only the table kernel is built for 13 / 24 workers)
-        if (g.workers == 13 && workers_env != 13) continue;          // (13 is chosen below)
-        if (workers_env && g.workers != workers_env) continue;
-        if (room_words(g) >= want || (!md.words_hint && stage_env <= 0 && g.workers == 12)) { geom = g; found = true; break; }
+    auto pick = [&]() -> TileGeom {
+        const TileGeom order[] = {{12, 2}, {13, 2}, {24, 1}, {8, 2}, {8, 1}};
+        TileGeom geom = order[3];
+        bool found = false;
+        for (const TileGeom g : order) {
+            if ((!lut || !md.delta) && (g.workers == 24 || g.workers == 13)) continue;   // (only the table kernel is built for 13 / 24 workers)
+            if (g.workers == 13 && workers_env != 13) continue;      // (13 is chosen below)
+            if (workers_env && g.workers != workers_env) continue;
+            if (room_words(g) >= want || (!md.words_hint && stage_env <= 0 && g.workers == 12)) { geom = g; found = true; break; }
+        }
+        if (!found && workers_env) for (const TileGeom g : order) if (g.workers == workers_env) { geom = g; break; }
+        return geom;
+    };
+    TileGeom geom = pick();
+    if (lut && !workers_env) {
+        // the table takes room from the staging: when that costs resident worker warps (long records, e.g.
+        // L = 7000 at RiceParameter 64: 1 x 8 instead of 2 x 8), the arithmetic front-end is the faster one
+        const size_t t = table;
+        lut = false; table = 0;
+        const TileGeom ga = pick();
+        if (ga.workers * ga.ctas > geom.workers * geom.ctas) geom = ga;
+        else { lut = true; table = t; }
     }
-    if (!found && workers_env) for (const TileGeom g : order) if (g.workers == workers_env) { geom = g; break; }
     // 12 or 13 workers: whichever leaves the smaller last round of tiles (cost = rounds of tiles x workers; C2:
     // 44 x 12 against 40 x 13, measured 0.550 against 0.543 ms)
     if (lut && geom.workers == 12 && geom.ctas == 2 && !workers_env && room_words({13, 2}) >= want) {

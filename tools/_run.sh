@@ -1,2 +1,5 @@
-python bench.py --steps 20 --warmup 3 > gpurun_out/r2f_c2.json 2> gpurun_out/r2f_c2.err
-python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/r2f_c2_ref.json 2> gpurun_out/r2f_c2_ref.err
+for M in 16 64; do
+DRICE_DEBUG=1 timeout 300 python tools/enc_time.py 76695 7000 $M 2000 10 2>&1 | grep -E "encode_tile|median" | tail -2 | cut -c1-150
+done
+DRICE_DEBUG=1 timeout 300 python tools/enc_time.py 153391 3500 64 2000 10 2>&1 | grep -E "encode_tile|median" | tail -2 | cut -c1-150
+DRICE_ENC_LUT=0 timeout 300 python tools/enc_time.py 153391 3500 64 2000 10 2>&1 | grep -E "encode_tile|median" | tail -1 | cut -c1-150
