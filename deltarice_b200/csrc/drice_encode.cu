@@ -11,22 +11,30 @@
 // around instructions per sample, not bytes.
 //
 // encode_tile_kernel (waves of <= 8192 samples), single pass over HBM:
-//   * persistent CTAs of NW worker warps + 1 control warp; a tile = NW consecutive waves taken from an
-//     atomic ticket; ONE WARP ENCODES ONE WAVE, 16 samples (8 packed int16x2 words) per lane and round;
-//     the next round's words are loaded between the round's front-end and its packing;
-//   * table front-end (RiceParameter 2 ... 64; encode_round_lut): t = delta + R (R = min(4M, 32)) on packed halves
-//     (PRMT / LOP3 / 2 x VIADD.16x2), the two (k+3)-bit fields become the offset of the pair's entry
+//   * persistent CTAs of NW worker warps + 1 control warp; a tile = NW consecutive waves; the first two
+//     tiles of a CTA are fixed by its block index, later ones come from an atomic ticket taken ONE TILE
+//     AHEAD, so that a worker knows its next wave while it still works on the current one; ONE WARP
+//     ENCODES ONE WAVE, 16 samples (8 packed int16x2 words) per lane and round; the next round's words
+//     are loaded between the round's front-end and its packing, the first round of the NEXT wave before
+//     the previous wave's copy-out (the loads fly during the copy-out and the tile barrier); a worker's
+//     wave state (position, size, record words) lives in shared memory between iterations, not in
+//     registers - registers are what bounds the kernel's occupancy;
+//   * table front-end (RiceParameter 2 ... 64; encode_round_lut): t = delta + R (R = min(4M, 32)) on packed
+//     halves (PRMT / LOP3 / 2 x VIADD.16x2), the two index fields become the offset of the pair's entry
 //     with LOP3 / IMAD / SHF, one LDS returns the pair's code | length << 24 from a skewed table in
 //     shared memory; pairs that hold an escape (a half outside the table) are redone per sample in a
 //     rare divergent path and their second code is appended after a per-position warp vote;
-//   * arithmetic front-end (every other parameter, pre-filtered input; encode_round): zig-zag on packed
-//     halves, two samples merged into one pair code with a single IMAD;
+//   * arithmetic front-end (every other parameter, pre-filtered input, or when the table would cost
+//     resident warps; encode_round): zig-zag on packed halves, two samples merged into one pair code
+//     with a single IMAD;
 //   * bit offsets: warp shuffle scan per round (the shuffle's own predicate guards the add), running
 //     base across rounds;
 //   * packing appends a code to a 64-bit window with IMAD.WIDE (acc * 2^len + value: the multiply IS
 //     the shift, and it runs on the FMA pipe) and emits finished 32-bit words to the warp's staging in
-//     shared memory; neighbouring lanes are stitched with one shuffle per round (the bits a lane leaves
-//     pending are OR-ed into the first word of the next lane): no shared-memory atomics;
+//     shared memory (a word is complete when bit 5 of the lane's running bit position flips: one LOP3
+//     sets the predicate of the three emit instructions); neighbouring lanes are stitched with one
+//     shuffle per round (the bits a lane leaves pending are OR-ed into the first word of the next
+//     lane): no shared-memory atomics;
 //   * cross-wave compaction without a second pass: the worker that finishes the tile's last wave
 //     publishes the tile's aggregate; the control warp resolves the tile's offset by decoupled look-back
 //     while the workers encode the next tile into their second staging buffer; the record
@@ -34,8 +42,10 @@
 //     writes the chunk header [total].  A wave larger than its staging is packed a second time straight
 //     into its record.
 //
-// Waves longer than one tile (L > 8192) use encode_multi_kernel: a sizing sweep, then a packing sweep
-// that re-reads the wave and streams completed words straight to HBM.
+// Waves longer than one tile (L > 8192): many of them - encode_multi_kernel, one CTA per wave (a sizing
+// sweep, then a packing sweep that re-reads the wave and streams completed words straight to HBM); a
+// few (the reference's long-wave chunkings, its default WaveformLength = -1) - the encode_long_* kernels,
+// several CTAs per wave (segment sizes, one-CTA scan, packing at the segments' bit offsets).
 #include "drice_kernels.cuh"
 
 #include <cstdio>
