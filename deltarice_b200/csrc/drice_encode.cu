@@ -830,7 +830,8 @@ __device__ __noinline__ void encode_wave_lut_in_place(const int16_t *wave, uint3
 // Shared control state lives in a ring of 3 slots (iteration % 3): a slot is reused only after
 // the workers have copied out the tile two iterations back, which needs the control warp to be
 // done with it.
-constexpr int kRing = 3;
+constexpr int kRing = 4;                                  // per-tile state: previous / current / next + one a fast worker has moved on to
+constexpr int kTileRing = 8;                              // tile indices, published three iterations ahead
 
 // NW worker warps (+ 1 control warp) per CTA: 12 for short waves (two CTAs per SM: measured best,
 // 0.69 vs 0.74 ms for 3 x 8 on C2; 13 and 14 lose to register pressure), 8 when the staging of
@@ -895,7 +896,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB)
 encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint32_t ntiles, uint32_t *const max_words)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ uint32_t s_tile[kRing];                   // tile index of the iteration
+    __shared__ volatile uint32_t s_tile[kTileRing];      // tile index of the iteration
+    __shared__ volatile uint32_t s_tseq[kTileRing];      // = iteration + 1 once s_tile holds that iteration's tile
     __shared__ uint32_t s_mine[kRing][NW];        // words each wave contributes
     __shared__ uint32_t s_cnt[kRing];                    // workers that have reported
     __shared__ uint32_t s_total[kRing];
@@ -908,7 +910,10 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
     if (threadIdx.x < kRing) { s_flag[threadIdx.x] = 0; s_cnt[threadIdx.x] = 0; }
     // the first two tiles of a CTA are fixed (all CTAs are resident and run iteration 0 together, so tiles
     // still start in index order); later ones come from the ticket counter, one iteration ahead
-    if (threadIdx.x == 0) { s_tile[0] = blockIdx.x; s_tile[1] = gridDim.x + blockIdx.x; }
+    if (threadIdx.x < kTileRing) {
+        s_tile[threadIdx.x] = threadIdx.x * gridDim.x + blockIdx.x;
+        s_tseq[threadIdx.x] = threadIdx.x < 3 ? threadIdx.x + 1 : 0;
+    }
     uint32_t tab = 0;                                    // shared address of the pair table (behind the staging)
     if constexpr (LUT != 0) {
         uint32_t *const tabp = smem + (size_t)(2 * NW) * stage_words;
@@ -922,7 +927,7 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
             const int slot = it % kRing;
             // sleeps on a named barrier (one per ring slot) until the tile's last worker arrives
             asm volatile("bar.sync %0, 64;" ::"r"(2 + slot) : "memory");
-            const uint32_t tile = s_tile[slot];
+            const uint32_t tile = s_tile[it % kTileRing];
             if (tile >= ntiles) break;
             const uint64_t mine = s_total[slot];
             const uint64_t excl = lookback_excl(p.lookback, tile, mine, lane);
@@ -951,7 +956,7 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
     __syncwarp();
     for (uint32_t it = 0;; ++it) {
         const int par = it & 1, slot = it % kRing;
-        const uint32_t tile = s_tile[slot];
+        const uint32_t tile = s_tile[it % kTileRing];
         const bool live = tile < ntiles;
         uint32_t next_ticket = 0;
         bool pre_next = false;
@@ -971,7 +976,7 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
             }
             // the tile after the next: taken as late as possible so that tiles start in ticket order; the
             // atomic's latency hides behind the copy-out below
-            if (threadIdx.x == 0) next_ticket = 2u * gridDim.x + atomicAdd(p.ticket, 1u);
+            if (threadIdx.x == 0) next_ticket = 3u * gridDim.x + atomicAdd(p.ticket, 1u);
             bool last = false;
             if (lane == 0) {
                 s_mine[slot][warp] = mine;
@@ -991,7 +996,9 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
             }
             if (__shfl_sync(0xffffffffu, last, 0))           // wakes the control warp
                 asm volatile("bar.arrive %0, 64;" ::"r"(2 + slot) : "memory");
-            setup_wave<NW, LUT>(p, s_tile[(it + 1) % kRing], ntiles, warp, lane, &s_wave[(it + 1) % kRing][warp], w0, pre_next);
+            // (the next tile's index was published two iterations ago by warp 0, which may lag this warp by one)
+            while (s_tseq[(it + 1) % kTileRing] != it + 2) __nanosleep(20);
+            setup_wave<NW, LUT>(p, s_tile[(it + 1) % kTileRing], ntiles, warp, lane, &s_wave[(it + 1) % kRing][warp], w0, pre_next);
         } else if (warp == 0) {
             __threadfence_block();
             asm volatile("bar.arrive %0, 64;" ::"r"(2 + slot) : "memory");   // lets the control warp see the end
@@ -1034,11 +1041,16 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
             __syncwarp();
         }
         if (!live) break;
-        // (slot (it + 2) % kRing was the previous tile's: warp 0 has seen the control warp finish with it above)
-        if (threadIdx.x == 0) s_tile[(it + 2) % kRing] = next_ticket;
+        if (threadIdx.x == 0) {
+            s_tile[(it + 3) % kTileRing] = next_ticket;
+            __threadfence_block();
+            s_tseq[(it + 3) % kTileRing] = it + 4;
+        }
         pre = pre_next;
-        // workers only (the control warp runs on its own clock)
-        asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+        __syncwarp();                                        // lane 0's wave slot, for the lanes of the next iteration
+        // No barrier between the workers: a worker moves on to its next wave at once.  What orders them is the
+        // copy-out above - it needs the tile's offset, i.e. every worker's wave of the PREVIOUS iteration - so a
+        // worker is never more than one iteration ahead of the slowest one (kRing = 4 slots of tile state).
     }
     if (lane == 0 && max_words && largest) atomicMax(max_words, largest);
 }
@@ -1585,18 +1597,17 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
     if (want < 64u) want = 64u;
     // room of a geometry: (227 KB - 1 KB reserved per CTA) / CTAs - static shared memory - table
     auto room_words = [&](TileGeom g) -> uint32_t {
-        const size_t per_cta = (size_t)(227 * 1024) / g.ctas - 1024 - (128 + 108 * (size_t)g.workers) - table;   // (static: ring + wave slots)
+        const size_t per_cta = (size_t)(227 * 1024) / g.ctas - 1024 - (160 + 144 * (size_t)g.workers) - table;   // (static: rings of tile state + wave slots)
         return (uint32_t)(per_cta / ((size_t)g.workers * 8)) & ~3u;
     };
     auto pick = [&]() -> TileGeom {
-        const TileGeom order[] = {{12, 2}, {13, 2}, {24, 1}, {8, 2}, {8, 1}};
-        TileGeom geom = order[3];
+        const TileGeom order[] = {{24, 1}, {12, 2}, {8, 2}, {8, 1}};
+        TileGeom geom = order[2];
         bool found = false;
         for (const TileGeom g : order) {
-            if ((!lut || !md.delta) && (g.workers == 24 || g.workers == 13)) continue;   // (only the table kernel is built for 13 / 24 workers)
-            if (g.workers == 13 && workers_env != 13) continue;      // (13 is chosen below)
+            if ((!lut || !md.delta) && g.workers == 24) continue;       // (only the table kernel is built for 24 workers)
             if (workers_env && g.workers != workers_env) continue;
-            if (room_words(g) >= want || (!md.words_hint && stage_env <= 0 && g.workers == 12)) { geom = g; found = true; break; }
+            if (room_words(g) >= want || (!md.words_hint && stage_env <= 0 && g.workers == (lut ? 24 : 12))) { geom = g; found = true; break; }
         }
         if (!found && workers_env) for (const TileGeom g : order) if (g.workers == workers_env) { geom = g; break; }
         return geom;
@@ -1610,13 +1621,6 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
         const TileGeom ga = pick();
         if (ga.workers * ga.ctas > geom.workers * geom.ctas) geom = ga;
         else { lut = true; table = t; }
-    }
-    // 12 or 13 workers: whichever leaves the smaller last round of tiles (cost = rounds of tiles x workers; C2:
-    // 44 x 12 against 40 x 13, measured 0.550 against 0.543 ms)
-    if (lut && geom.workers == 12 && geom.ctas == 2 && !workers_env && room_words({13, 2}) >= want) {
-        const uint64_t ctas = 2ull * (uint64_t)g_num_sms;
-        const uint64_t c12 = ((p.nwaves + ctas * 12 - 1) / (ctas * 12)) * 12, c13 = ((p.nwaves + ctas * 13 - 1) / (ctas * 13)) * 13;
-        if (c13 < c12) geom.workers = 13;
     }
     uint32_t stage = room_words(geom) < want ? room_words(geom) : want;
     if (!md.words_hint && stage_env <= 0) stage = room_words(geom) < worst ? room_words(geom) : worst;   // no hint: all the room
@@ -1644,11 +1648,10 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
         if (grid > ntiles) grid = ntiles;
         kernel<<<grid, nthreads, smem, st>>>(p, stage, ntiles, md.max_words);
     };
-    static DeviceOnce a12, a8, a8n, t12, t13, t24, t8;                // per K (this function is a template)
+    static DeviceOnce a12, a8, a8n, t12, t24, t8;                // per K (this function is a template)
     if constexpr (LutConst<K>::kOk) {
         if (lut) {
             if (geom.workers == 12) launch(encode_tile_kernel<K, 2, true, 12, 1>, t12, 12);
-            else if (geom.workers == 13) launch(encode_tile_kernel<K, 2, true, 13, 1>, t13, 13);
             else if (geom.workers == 24) launch(encode_tile_kernel<K, 1, true, 24, 1>, t24, 24);
             else launch(encode_tile_kernel<K, 2, true, 8, 1>, t8, 8);
             return 1;

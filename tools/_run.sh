@@ -1,2 +1,6 @@
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:encode_tile -s 4 -c 1 -o gpurun_out/r2f_enc_c2 -f python tools/enc_time.py 153391 3500 4 2000 2 > gpurun_out/r2f_ncu4.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:encode_tile -s 4 -c 1 -o gpurun_out/r2f_enc_c3m8 -f python tools/enc_time.py 76695 7000 8 2000 2 > gpurun_out/r2f_ncu5.log 2>&1
+timeout 300 python tools/enc_time.py 153391 3500 4 2000 20 2>&1 | tail -1 | cut -c1-200
+timeout 300 python tools/enc_time.py 76695 7000 8 2000 20 2>&1 | tail -1 | cut -c1-100
+timeout 300 python tools/enc_time.py 153391 3500 256 2000 20 2>&1 | tail -1 | cut -c1-100
+timeout 300 python tools/enc_time.py 2000 7000 8 2000 20 2>&1 | tail -1 | cut -c1-100
+timeout 300 python tools/enc_time.py 20 7000 8 20 20 2>&1 | tail -1 | cut -c1-100
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
