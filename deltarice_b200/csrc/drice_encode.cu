@@ -1605,9 +1605,9 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
         TileGeom geom = order[2];
         bool found = false;
         for (const TileGeom g : order) {
-            if ((!lut || !md.delta) && g.workers == 24) continue;       // (only the table kernel is built for 24 workers)
+            if (!md.delta && g.workers == 24) continue;                // (no 24-worker kernel without the delta)
             if (workers_env && g.workers != workers_env) continue;
-            if (room_words(g) >= want || (!md.words_hint && stage_env <= 0 && g.workers == (lut ? 24 : 12))) { geom = g; found = true; break; }
+            if (room_words(g) >= want || (!md.words_hint && stage_env <= 0 && g.workers == (md.delta ? 24 : 12))) { geom = g; found = true; break; }
         }
         if (!found && workers_env) for (const TileGeom g : order) if (g.workers == workers_env) { geom = g; break; }
         return geom;
@@ -1648,7 +1648,7 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
         if (grid > ntiles) grid = ntiles;
         kernel<<<grid, nthreads, smem, st>>>(p, stage, ntiles, md.max_words);
     };
-    static DeviceOnce a12, a8, a8n, t12, t24, t8;                // per K (this function is a template)
+    static DeviceOnce a12, a24, a8, a8n, t12, t24, t8;                // per K (this function is a template)
     if constexpr (LutConst<K>::kOk) {
         if (lut) {
             if (geom.workers == 12) launch(encode_tile_kernel<K, 2, true, 12, 1>, t12, 12);
@@ -1658,6 +1658,7 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
         }
     }
     if (!md.delta) launch(encode_tile_kernel<K, 2, false, 8>, a8n, 8);    // no delta (filter [1] / pre-filtered input)
+    else if (geom.workers == 24) launch(encode_tile_kernel<K, 1, true, 24>, a24, 24);
     else if (geom.workers == 12) launch(encode_tile_kernel<K, 2, true, 12>, a12, 12);
     else launch(encode_tile_kernel<K, 2, true, 8>, a8, 8);
     return 1;
