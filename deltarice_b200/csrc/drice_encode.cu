@@ -1007,7 +1007,7 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
         const int ps = (it + kRing - 1) % kRing;
         const WaveSlot *const wp = &s_wave[ps][warp];
         if (it > 0 && wp->flags) {
-            while (s_flag[ps] != it) __nanosleep(40);        // tile offset: normally there long ago
+            while (s_flag[ps] != it) __nanosleep(100);        // tile offset: normally there long ago
             __threadfence_block();
             const uint32_t v = lane < NW ? s_mine[ps][lane] : 0u;
             const uint32_t loff = __reduce_add_sync(0xffffffffu, lane < warp ? v : 0u);
