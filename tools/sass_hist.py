@@ -3,7 +3,7 @@ usage: python tools/sass_hist.py > profiles/r2_sass_hist.txt"""
 import collections, glob, os, re, subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOT = [  # (object glob, mangled-name regex, label)
-    ("drice_encode_p0.o", r"encode_tile_kernelILi2ELi2ELb1ELi12ELi1E", "encode_tile_kernel<K=2, 2 CTAs/SM, delta, 12 workers, table front-end>  (C2: M = 4)"),
+    ("drice_encode_p0.o", r"encode_tile_kernelILi2ELi1ELb1ELi24ELi1E", "encode_tile_kernel<K=2, 1 CTA/SM, delta, 24 workers, table front-end>  (C2: M = 4)"),
     ("drice_encode_p0.o", r"encode_tile_kernelILi3ELi1ELb1ELi24ELi1E", "encode_tile_kernel<K=3, 1 CTA/SM, delta, 24 workers, table front-end>  (C3/C5: M = 8, L = 7000)"),
     ("drice_encode_p1.o", r"encode_tile_kernelILi4ELi2ELb1ELi12ELi0E", "encode_tile_kernel<K=4, arithmetic front-end>  (M = 16)"),
     ("drice_encode_p0.o", r"encode_long_pack_kernelILi3E", "encode_long_pack_kernel<K=3>  (few long waves)"),
