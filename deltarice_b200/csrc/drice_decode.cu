@@ -725,11 +725,21 @@ __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const Par
     const uint64_t lim_al = p.comp_words + mis;             // end of the stream, aligned-relative
     const uint32_t ngroups = (p.nwaves + 31u) / 32u;
 
+    // A warp's first task is fixed (warp-major over the CTAs), later ones come from the ticket counter: a batch of
+    // about one task per resident warp (C2: 4794 tasks, 5032 warps) then spreads evenly over the SMs (32 or 33
+    // tasks each) instead of as the atomics happen to be served (up to 34: the busiest SM sets the time).
+    bool first_task = true;
     while (true) {
         uint32_t grp = 0;
-        if (lane == 0) grp = atomicAdd(p.ticket, 1u);
-        grp = __shfl_sync(0xffffffffu, grp, 0);
-        if (grp >= ngroups) break;
+        if (first_task) {
+            grp = (uint32_t)warp * gridDim.x + blockIdx.x;
+            first_task = false;
+            if (grp >= ngroups) continue;                    // (nothing left in the fixed part: try the counter)
+        } else {
+            if (lane == 0) grp = nwarps * gridDim.x + atomicAdd(p.ticket, 1u);
+            grp = __shfl_sync(0xffffffffu, grp, 0);
+            if (grp >= ngroups) break;
+        }
         const uint32_t g = grp * 32 + lane;
         const bool active = g < p.nwaves;
         const uint32_t n = active ? __ldg(p.wave_n + g) : 0u;
