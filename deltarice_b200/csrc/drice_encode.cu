@@ -1601,13 +1601,17 @@ int launch_k(const EncodeParams &p, const EncodeMode &md, uint32_t max_wave_len,
         return (uint32_t)(per_cta / ((size_t)g.workers * 8)) & ~3u;
     };
     auto pick = [&]() -> TileGeom {
-        const TileGeom order[] = {{24, 1}, {12, 2}, {8, 2}, {8, 1}};
-        TileGeom geom = order[2];
+        // small batches (up to two rounds of 2 x 8-wave tiles per SM): tiles of 8 waves spread over more SMs and
+        // finish sooner (2000 x 7000: 0.045 against 0.052 ms; 20 x 7000: 0.038 against 0.045)
+        const bool small = !workers_env && p.nwaves <= 32u * (uint32_t)g_num_sms;
+        const TileGeom order_big[] = {{24, 1}, {12, 2}, {8, 2}, {8, 1}}, order_small[] = {{8, 2}, {8, 1}, {8, 1}, {8, 1}};
+        const TileGeom (&order)[4] = small ? order_small : order_big;
+        TileGeom geom = small ? order[1] : order[2];
         bool found = false;
         for (const TileGeom g : order) {
             if (!md.delta && g.workers == 24) continue;                // (no 24-worker kernel without the delta)
             if (workers_env && g.workers != workers_env) continue;
-            if (room_words(g) >= want || (!md.words_hint && stage_env <= 0 && g.workers == (md.delta ? 24 : 12))) { geom = g; found = true; break; }
+            if (room_words(g) >= want || (!md.words_hint && stage_env <= 0 && g.workers == (small ? 8 : md.delta ? 24 : 12))) { geom = g; found = true; break; }
         }
         if (!found && workers_env) for (const TileGeom g : order) if (g.workers == workers_env) { geom = g; break; }
         return geom;
