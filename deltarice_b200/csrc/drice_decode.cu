@@ -1034,8 +1034,9 @@ __host__ __device__ __forceinline__ uint64_t long_worst_words(uint64_t n) { retu
 
 template <bool IDENT>
 __global__ void __launch_bounds__(kWideThreads, 1)
-parse_long_kernel(const ParseParams p, const uint32_t segs_per_wave, const uint32_t nitems, unsigned long long *const state)
-{
+parse_long_kernel(const ParseParams p, const uint32_t segs_per_wave, const uint32_t nitems, unsigned long long *const state,
+                  const uint32_t seg_words)
+{   // seg_words: words per segment (a multiple of kWideRunWords, <= kWideMaxWords; chosen per batch by parse_long_plan)
     constexpr int NT = kWideThreads;
     extern __shared__ __align__(16) uint32_t wsm[];
     uint32_t *words = wsm;                                       // kWideMaxWords + 4 (the last run looks past the segment)
@@ -1069,9 +1070,9 @@ parse_long_kernel(const ParseParams p, const uint32_t segs_per_wave, const uint3
             if (threadIdx.x == 0 && sg == 0) atomicOr(p.status, kErrStream);
             continue;
         }
-        const uint64_t w0 = (uint64_t)sg * kWideMaxWords;
+        const uint64_t w0 = (uint64_t)sg * seg_words;
         if (w0 >= nw) continue;                                  // the record has fewer segments
-        const uint32_t nseg = (uint32_t)((nw - w0) < (uint64_t)kWideMaxWords ? (nw - w0) : (uint64_t)kWideMaxWords);
+        const uint32_t nseg = (uint32_t)((nw - w0) < (uint64_t)seg_words ? (nw - w0) : (uint64_t)seg_words);
         const bool last_seg = w0 + nseg == nw;
         int16_t *out = p.out + p.wave_out[g];
         for (uint32_t i = threadIdx.x; i < nseg + 4; i += NT) words[i] = (w0 + i < nw) ? p.comp[rec + 1 + w0 + i] : 0u;
@@ -1167,7 +1168,9 @@ parse_long_kernel(const ParseParams p, const uint32_t segs_per_wave, const uint3
         const unsigned long long idx0 = s_idx0;
         unsigned long long idx = idx0 + bc + ic - c;             // sample index of the thread's first code
         uint32_t acc = s_acc0 + bd + id - dsm;                   // running sample before it (src/deltaRice.c:84-89)
-        bool bad = threadIdx.x == 0 && ((last_seg && idx0 + total < n) || (!last_seg && idx0 + total >= n));
+        // (a wave's last code may start in one segment and end in the next, which is then the record's last: a
+        // segment that is not the last one may hold exactly the remaining codes, but not more)
+        bool bad = threadIdx.x == 0 && ((last_seg && idx0 + total < n) || (!last_seg && idx0 + total > n));
         // ---- the samples --------------------------------------------------------------------------
         for (uint32_t r = r0; r < r1 && idx < n; ++r) {
             const uint32_t end = (r + 1) * (kWideRunWords * 32);
@@ -1179,17 +1182,44 @@ parse_long_kernel(const ParseParams p, const uint32_t segs_per_wave, const uint3
                 bad |= !cd.valid;
                 out[idx] = (int16_t)(IDENT ? (uint32_t)cd.delta : acc);
                 ++idx;
-                if (idx == n) bad |= !last_seg || ((pos + 31u) >> 5) != nseg;   // the codes must end inside the record's last word
+                if (idx == n) bad |= (uint64_t)((pos + 31u) >> 5) != (uint64_t)nw - w0;   // the codes must end inside the record's last word
             }
         }
         if (bad) atomicOr(p.status, kErrStream);
     }
 }
 
-// work items of parse_long_kernel for a batch (0: the batch does not take that path)
-uint32_t parse_long_segments(uint32_t max_n)
+// Segments of parse_long_kernel for a batch.  The host only knows the WORST record size (25 bits per sample; real
+// records are about a quarter of it), so the segment is sized for ~6 worst-case items per SM - one to two real
+// ones: long waves get segments of up to kWideMaxWords, a handful of SHORT waves (one HDF5 chunk of the README's
+// 20 x 7000) is cut into segments of >= 256 words as well instead of one CTA per wave (parse_wide_kernel).
+struct LongPlan { uint32_t seg_words, segs; };
+LongPlan parse_long_plan(uint32_t nwaves, uint32_t max_n, int sms)
 {
-    return (uint32_t)((long_worst_words(max_n) + kWideMaxWords - 1) / kWideMaxWords);
+    const uint64_t worst = long_worst_words(max_n);
+    uint64_t sw = (worst * (uint64_t)nwaves + 6ull * (uint64_t)sms - 1) / (6ull * (uint64_t)sms);
+    sw = (sw + 63ull) & ~63ull;
+    if (sw < 256ull) sw = 256ull;
+    if (sw > (uint64_t)kWideMaxWords) sw = (uint64_t)kWideMaxWords;
+    LongPlan pl;
+    pl.seg_words = (uint32_t)sw;
+    pl.segs = (uint32_t)((worst + sw - 1) / sw);
+    return pl;
+}
+// does the batch take parse_long_kernel?  (waves longer than 8192 samples always, shorter ones when the plan
+// cuts them into at least 16 worst-case segments, i.e. about four real ones)
+bool parse_long_applies(uint32_t nwaves, uint32_t max_n, int sms, LongPlan *pl)
+{
+    static long wide = -1;                                   // DRICE_PARSE_WIDE=<max waves> (0: always one lane per wave)
+    if (wide < 0) {
+        const char *e = getenv("DRICE_PARSE_WIDE");
+        wide = e ? atol(e) : (long)kWideMaxWaves;
+    }
+    static const int short_env = [] { const char *v = getenv("DRICE_PARSE_LONG_SHORT"); return v ? atoi(v) : 1; }();
+    if ((long)nwaves > wide || nwaves == 0) return false;
+    *pl = parse_long_plan(nwaves, max_n, sms);
+    if (max_n > 8192u) return true;
+    return short_env != 0 && pl->segs >= 16u;                // (20 x 7000: 74 -> 52 us; from ~50 waves on one CTA per wave is as fast)
 }
 
 // warps per SM: as many as fit, trimmed so that the last round of warp tasks is nearly full
@@ -1227,7 +1257,8 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
             const char *e = getenv("DRICE_PARSE_WIDE");
             wide = e ? atol(e) : (long)kWideMaxWaves;
         }
-        if ((long)p.nwaves <= wide && p.max_n > 8192u && p.long_state) {
+        LongPlan pl;
+        if (p.long_state && parse_long_applies(p.nwaves, p.max_n, g_dec_sms, &pl)) {
             static DeviceOnce lattr;
             const size_t lsmem = (size_t)(kWideMaxWords + 4 + (1 << kWideLutBits) + 2 * kWideThreads) * 4 +
                                  (size_t)kWideMaxRuns * 32 + kWideMaxRuns + 16 + 2 * kLongGroups * 32 + 16;
@@ -1235,11 +1266,10 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
                 cudaFuncSetAttribute(parse_long_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
                 cudaFuncSetAttribute(parse_long_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
             }
-            const uint32_t segs = parse_long_segments(p.max_n);
-            const uint64_t nitems = (uint64_t)p.nwaves * segs;
+            const uint64_t nitems = (uint64_t)p.nwaves * pl.segs;
             const uint32_t lgrid = nitems < (uint64_t)g_dec_sms ? (uint32_t)nitems : (uint32_t)g_dec_sms;
-            if (p.identity) parse_long_kernel<true><<<lgrid, kWideThreads, lsmem, st>>>(p, segs, (uint32_t)nitems, p.long_state);
-            else            parse_long_kernel<false><<<lgrid, kWideThreads, lsmem, st>>>(p, segs, (uint32_t)nitems, p.long_state);
+            if (p.identity) parse_long_kernel<true><<<lgrid, kWideThreads, lsmem, st>>>(p, pl.segs, (uint32_t)nitems, p.long_state, pl.seg_words);
+            else            parse_long_kernel<false><<<lgrid, kWideThreads, lsmem, st>>>(p, pl.segs, (uint32_t)nitems, p.long_state, pl.seg_words);
             return 1;
         }
         if ((long)p.nwaves <= wide && p.max_n <= 8192u) {
@@ -1311,13 +1341,9 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
 // zeroed state (bytes) parse_long_kernel needs for a batch; 0 when the batch does not take that path
 size_t parse_long_state_bytes(uint32_t nwaves, uint32_t max_n)
 {
-    static long wide = -1;
-    if (wide < 0) {
-        const char *e = getenv("DRICE_PARSE_WIDE");
-        wide = e ? atol(e) : (long)kWideMaxWaves;
-    }
-    if ((long)nwaves > wide || max_n <= 8192u) return 0;
-    const uint64_t items = (uint64_t)nwaves * parse_long_segments(max_n);
+    LongPlan pl;
+    if (!parse_long_applies(nwaves, max_n, device_sm_count(), &pl)) return 0;
+    const uint64_t items = (uint64_t)nwaves * pl.segs;
     if (items >= (1ull << 31)) return 0;
     return (size_t)items * 16;
 }

@@ -321,6 +321,48 @@ def test_long_waves(codec, oracle, M, L, sizes, sigma):
     assert np.array_equal(codec.decode_host(want.view(np.uint8), wboff, off, M, L), x)
 
 
+def _code_bits(x, k):
+    """Bits of every sample's code (delta from the previous sample of the wave, src/deltaRice.c:207-228)."""
+    d = np.diff(x.astype(np.int64), prepend=0)
+    d = ((d + 32768) % 65536) - 32768
+    u = np.where(d >= 0, 2 * d, -2 * d - 1)
+    q = u >> k
+    return np.where(q >= 8, 25, q + k + 1)
+
+
+@pytest.mark.parametrize("L,total_hint", [(6000, 4), (None, 1)])
+def test_last_code_straddles_a_segment(codec, oracle, L, total_hint):
+    """parse_long_kernel cuts records into segments (256 words for a handful of waves): a wave whose LAST code starts
+    in one segment and ends in the next - which then holds nothing but that code's tail - is a valid record."""
+    k, M = 3, 8
+    r = np.random.default_rng(11)
+    tail = np.clip(np.rint(np.cumsum(r.normal(0, 6, 40000))), -32768, 32767).astype(np.int16)
+    cum = np.cumsum(_code_bits(tail, k))
+    # last sample i whose code covers a multiple of 8192 bits (256 words) strictly inside it
+    cover = np.nonzero((np.concatenate([[0], cum[:-1]]) // 8192) < ((cum - 1) // 8192))[0]
+    cover = cover[(cum[cover] % 8192) != 0]
+    cases = [int(cover[0]) + 1, int(cover[len(cover) // 2]) + 1] if L is None else [int(cover[0]) + 1]
+    for n0 in cases:
+        if L is None:
+            x = tail[:n0].copy()                                     # the whole chunk is one wave of n0 samples
+        else:
+            lead = r.normal(0, 6, L * (total_hint - 1)).astype(np.int16)
+            x = np.concatenate([lead, tail[:n0]])                    # ... the chunk's short last wave
+            assert n0 < L
+        off = np.array([0, x.size], dtype=np.uint64)
+        want = oracle.encode_chunk(x, M, L)
+        assert int(want[-(int(np.ceil(cum[n0 - 1] / 32))) - 1]) == int(np.ceil(cum[n0 - 1] / 32))   # the last record is the crafted wave
+        assert (int(np.ceil(cum[n0 - 1] / 32)) - 1) % 256 == 0      # ... and its last word starts a segment
+        got, boff = codec.encode_host(x, off, M, L)
+        assert np.array_equal(got.view(np.uint32), want)
+        assert np.array_equal(codec.decode_host(want.view(np.uint8), None, off, M, L), x)
+        # a word too many / too few behind it is still an error
+        import deltarice_b200 as d
+        extra = np.concatenate([want, np.zeros(1, np.uint32)]); extra[-(int(np.ceil(cum[n0 - 1] / 32))) - 2] += 1
+        with pytest.raises(d.DeltaRiceError):
+            codec.decode_host(extra.view(np.uint8), None, off, M, L)
+
+
 def test_long_wave_capacity_and_filter(codec, oracle):
     """The several-CTAs-per-wave encoder: an output buffer that is too small is reported (nothing is written
     past it), and option tuples whose pre-filter is [1] (no delta) take the same kernels."""

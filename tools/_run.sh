@@ -1,3 +1,3 @@
-for r in 20 2000 4000 5000; do DRICE_DEBUG=1 python tools/enc_time.py $r 7000 8 2000 50 2>&1 | grep -E "encode_tile|median" | tail -2 | cut -c1-110; done
-python tools/small_chunk_breakdown.py 20 2>&1 | tail -8 | cut -c1-160
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "straddles or long" 2>&1 | tail -15
+python tools/small_chunk_breakdown.py 20 2>&1 | grep -E "decode|kernel times" | cut -c1-200
+python tools/small_chunk_breakdown.py 60 2>&1 | grep -E "device-resident decode|kernel times" | cut -c1-200
