@@ -678,8 +678,13 @@ extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_co
     const size_t nw = g.nwaves;
     // scratch: [parse ticket, 16 B][chain state of the long-wave parser] (zeroed) | wave tables
     const size_t long_bytes = parse_long_state_bytes(g.nwaves, g.max_wave);
-    const size_t zeroed = 16 + long_bytes;
-    const size_t scratch = zeroed + nw * (8 + 8 + 4) + 64 + 16;
+    // [.. | 16 counters of the density sort] (zeroed) | wave tables | the sort's permutation
+    const size_t zeroed = 16 + long_bytes + 64;
+    // batches whose records are heavy on average (more than k + 5 bits per sample: escapes) are decoded with
+    // waves of similar density sharing a warp (drice_decode.cu: wave_hist_kernel / wave_scatter_kernel)
+    static const int sort_env = [] { const char *v = getenv("DRICE_DEC_SORT"); return v ? atoi(v) : 1; }();
+    const bool dense = sort_env == 2 || (sort_env == 1 && (woff[nchunks] - woff[0]) * 32ull > (off[nchunks] - off[0]) * (uint64_t)(k + 5));
+    const size_t scratch = zeroed + nw * (8 + 8 + 4) + 64 + 16 + (dense ? nw * 4 + 16 : 0);
     if (scratch > ctx->d_scratch.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
     DR_CUDA(ctx, ctx->d_scratch.reserve(scratch));
     uint64_t *d_soff, *d_woff64;
@@ -730,6 +735,8 @@ extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_co
     pp.k = k;
     pp.identity = ctx->filter_mode != 0;
     pp.long_state = long_bytes ? (unsigned long long *)((char *)ctx->d_scratch.p + 16) : nullptr;
+    pp.sort_counters = (uint32_t *)((char *)ctx->d_scratch.p + 16 + long_bytes);
+    pp.sort_perm = dense ? (uint32_t *)(((uintptr_t)(wave_n + nw) + 15) & ~(uintptr_t)15) : nullptr;
     // widest store that every wave start allows
     int store_bytes = (int)(g.align_samples * 2);
     while (store_bytes > 2 && (reinterpret_cast<uintptr_t>(d_out) & (uintptr_t)(store_bytes - 1))) store_bytes >>= 1;

@@ -687,7 +687,7 @@ __device__ __forceinline__ void group(LaneDec &d, uint32_t ring_b, uint32_t lutl
     if ((FIRST + N) & 1) carry = st[N - 1];
 }
 
-template <bool W10, bool IDENT>
+template <bool W10, bool IDENT, bool HEAVY>
 __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const ParseParams p)
 {
     extern __shared__ __align__(16) uint32_t dsm[];
@@ -740,13 +740,19 @@ __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const Par
             grp = __shfl_sync(0xffffffffu, grp, 0);
             if (grp >= ngroups) break;
         }
-        const uint32_t g = grp * 32 + lane;
-        const bool active = g < p.nwaves;
+        const uint32_t slot = grp * 32 + lane;
+        const bool active = slot < p.nwaves;
+        const uint32_t g = (active && p.sort_perm) ? __ldg(p.sort_perm + slot) : slot;
         const uint32_t n = active ? __ldg(p.wave_n + g) : 0u;
         const uint64_t rec = active ? __ldg(p.wave_in + g) : 0ull;        // word index of [nwords]
         const uint64_t obase = active ? __ldg(p.wave_out + g) : 0ull;     // sample offset of the wave
         const uint32_t nwords = n ? __ldg(p.comp + rec) : 0u;
         int16_t *optr = p.out + obase;
+        // A warp whose waves are heavy (more than k + 3.5 bits per sample: an escape in most groups of codes) skips the
+        // table: a group with a miss is redone code by code anyway, by its lane while the others wait, so the table
+        // attempt is pure overhead there.  (Warp uniform; with the density sort the warps are homogeneous.)
+        const bool dens = n && (uint64_t)nwords * 256ull > (uint64_t)n * (uint32_t)(8 * k + 28);
+        const bool heavy = HEAVY && __popc(__ballot_sync(0xffffffffu, dens)) >= 8;   // (HEAVY: the instance for dense batches)
 
         RingFeed rf;
         rf.base_al = (rec + 1 + mis) & ~7ull;               // aligned-relative index of the sector holding the first code word
@@ -817,7 +823,16 @@ __global__ void __launch_bounds__(kParseMaxWarps * 32, 2) parse_kernel(const Par
                 // 16 samples as groups of N codes per window (N * W <= 64): 6+5+5 for W <= 10, else 4x4
                 uint32_t o[8];
                 uint32_t carry = 0;
-                if (W10) {
+                if (heavy) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t Sb = d.S;
+                        d.one(ring_b, k, kmask);
+                        const uint32_t stv = IDENT ? d.S - Sb : d.S;
+                        if (i & 1) o[i >> 1] = prmt(carry, stv, 0x7632);
+                        else carry = stv;
+                    }
+                } else if (W10) {
                     group<6, 0, IDENT>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
                     group<5, 6, IDENT>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
                     group<5, 11, IDENT>(d, ring_b, lutl, imask, ish, k, kmask, o, carry);
@@ -1236,19 +1251,85 @@ int pick_parse_warps(uint32_t ngroups, int sms, int max_warps)
     return best;
 }
 
+// ------------------------------------------------------------------------------------
+// waves sorted by density for the lane parser
+// ------------------------------------------------------------------------------------
+// The 32 lanes of a warp advance in lock step, and a group of codes with an escape (or any code longer than
+// the table's window) is redone by its lane while the others wait: a warp is as slow as its heaviest wave.
+// When a batch mixes noise levels (BASELINE config C4), waves of similar bits per sample are put into the
+// same warps instead: a counting sort into 8 buckets of (record words * 32 / samples) relative to k - a
+// histogram pass and a scatter pass over the wave table (order inside a bucket is arbitrary, tiles of
+// consecutive waves stay together).  Only the ORDER in which waves are decoded changes.
+constexpr int kSortBuckets = 8;
+constexpr int kSortThreads = 256, kSortPerThread = 4;
+__device__ __forceinline__ uint32_t density_bucket(const ParseParams &p, uint32_t g)
+{
+    const uint32_t n = __ldg(p.wave_n + g);
+    const uint64_t rec = __ldg(p.wave_in + g);
+    if (n == 0 || rec >= p.comp_words) return 0;
+    const uint64_t nw = __ldg(p.comp + rec);
+    const uint64_t x8 = nw * 256ull / n;                     // bits per sample, in eighths
+    const uint32_t k8 = (uint32_t)p.k * 8u;
+    const uint32_t t[kSortBuckets - 1] = {k8 + 20u, k8 + 28u, k8 + 40u, k8 + 56u, k8 + 80u, k8 + 112u, k8 + 152u};
+    uint32_t b = 0;
+#pragma unroll
+    for (int i = 0; i < kSortBuckets - 1; ++i) b += x8 > t[i];
+    return b;
+}
+__global__ void __launch_bounds__(kSortThreads) wave_hist_kernel(const ParseParams p)
+{
+    __shared__ uint32_t h[kSortBuckets];
+    if (threadIdx.x < kSortBuckets) h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t g0 = blockIdx.x * (kSortThreads * kSortPerThread);
+#pragma unroll
+    for (int i = 0; i < kSortPerThread; ++i) {
+        const uint32_t g = g0 + i * kSortThreads + threadIdx.x;
+        if (g < p.nwaves) atomicAdd(&h[density_bucket(p, g)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < kSortBuckets && h[threadIdx.x]) atomicAdd(p.sort_counters + threadIdx.x, h[threadIdx.x]);
+}
+__global__ void __launch_bounds__(kSortThreads) wave_scatter_kernel(const ParseParams p)
+{
+    __shared__ uint32_t h[kSortBuckets], base[kSortBuckets];
+    if (threadIdx.x < kSortBuckets) h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t g0 = blockIdx.x * (kSortThreads * kSortPerThread);
+    uint32_t b[kSortPerThread], r[kSortPerThread];
+#pragma unroll
+    for (int i = 0; i < kSortPerThread; ++i) {
+        const uint32_t g = g0 + i * kSortThreads + threadIdx.x;
+        b[i] = 0; r[i] = 0;
+        if (g < p.nwaves) { b[i] = density_bucket(p, g); r[i] = atomicAdd(&h[b[i]], 1u); }
+    }
+    __syncthreads();
+    if (threadIdx.x < kSortBuckets) {
+        uint32_t start = 0;                                  // first slot of the bucket: buckets before it (histogram pass)
+        for (int j = 0; j < (int)threadIdx.x; ++j) start += p.sort_counters[j];
+        base[threadIdx.x] = start + (h[threadIdx.x] ? atomicAdd(p.sort_counters + kSortBuckets + threadIdx.x, h[threadIdx.x]) : 0u);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kSortPerThread; ++i) {
+        const uint32_t g = g0 + i * kSortThreads + threadIdx.x;
+        if (g < p.nwaves) p.sort_perm[base[b[i]] + r[i]] = g;
+    }
+}
+
 int launch_parse_impl(const ParseParams &p, cudaStream_t st)
 {
     const int g_dec_sms = device_sm_count();
     static DeviceOnce attr_set;                          // (function attributes belong to a device)
     if (attr_set.first()) {
-        cudaFuncSetAttribute(parse_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-        cudaFuncSetAttribute(parse_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(parse_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-        cudaFuncSetAttribute(parse_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(parse_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-        cudaFuncSetAttribute(parse_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(parse_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-        cudaFuncSetAttribute(parse_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        auto opt_in = [](auto kern) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        };
+        opt_in(parse_kernel<true, false, false>); opt_in(parse_kernel<false, false, false>);
+        opt_in(parse_kernel<true, true, false>);  opt_in(parse_kernel<false, true, false>);
+        opt_in(parse_kernel<true, false, true>);  opt_in(parse_kernel<false, false, true>);
+        opt_in(parse_kernel<true, true, true>);   opt_in(parse_kernel<false, true, true>);
     }
     // small batches: one CTA per wave (parallel inside the wave) instead of one lane per wave
     {
@@ -1320,20 +1401,33 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
     off = lut_at + kLutBytes + nabove * kRingBytes;
     ParseParams pp = p;
     pp.smem_bytes = (uint32_t)(off - 1024);
+    int launches = 1;
+    if (pp.sort_perm && pp.sort_counters) {
+        const uint32_t sgrid = (p.nwaves + kSortThreads * kSortPerThread - 1) / (kSortThreads * kSortPerThread);
+        wave_hist_kernel<<<sgrid, kSortThreads, 0, st>>>(pp);
+        wave_scatter_kernel<<<sgrid, kSortThreads, 0, st>>>(pp);
+        launches += 2;
+    } else {
+        pp.sort_perm = nullptr;
+    }
     if (getenv("DRICE_DEBUG")) {
         int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, parse_kernel<true, false>, warps * 32, pp.smem_bytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, parse_kernel<true, false, false>, warps * 32, pp.smem_bytes);
         fprintf(stderr, "parse: grid %u warps %d smem %u occ %d\n", grid, warps, pp.smem_bytes, occ);
     }
     const bool w10 = lut_bits_for(p.k) <= 10;
-    if (p.identity) {
-        if (w10) parse_kernel<true, true><<<grid, warps * 32, pp.smem_bytes, st>>>(pp);
-        else     parse_kernel<false, true><<<grid, warps * 32, pp.smem_bytes, st>>>(pp);
+    // dense batches (the ones that are sorted): the instance whose heavy warps skip the table
+    static const int heavy_env = [] { const char *v = getenv("DRICE_DEC_HEAVY"); return v ? atoi(v) : 1; }();
+    const bool hv = pp.sort_perm != nullptr && heavy_env != 0;
+    auto go = [&](auto kern) { kern<<<grid, warps * 32, pp.smem_bytes, st>>>(pp); };
+    if (hv) {
+        if (p.identity) { if (w10) go(parse_kernel<true, true, true>); else go(parse_kernel<false, true, true>); }
+        else            { if (w10) go(parse_kernel<true, false, true>); else go(parse_kernel<false, false, true>); }
     } else {
-        if (w10) parse_kernel<true, false><<<grid, warps * 32, pp.smem_bytes, st>>>(pp);
-        else     parse_kernel<false, false><<<grid, warps * 32, pp.smem_bytes, st>>>(pp);
+        if (p.identity) { if (w10) go(parse_kernel<true, true, false>); else go(parse_kernel<false, true, false>); }
+        else            { if (w10) go(parse_kernel<true, false, false>); else go(parse_kernel<false, false, false>); }
     }
-    return 1;
+    return launches;
 }
 
 }  // namespace

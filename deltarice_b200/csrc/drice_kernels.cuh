@@ -97,6 +97,10 @@ struct ParseParams {
     int             k;
     int             identity;           // 1: write the decoded values themselves (no inverse delta)
     unsigned long long *long_state;     // zeroed, parse_long_state_bytes(): chain state of the long-wave parser (or null)
+    // lane parser, batches with heavy records: waves sorted by bits per sample (null: waves in order).
+    // sort_perm: [nwaves] scratch; sort_counters: 16 zeroed words (histogram + cursors of 8 buckets)
+    uint32_t       *sort_perm;
+    uint32_t       *sort_counters;
 };
 
 // ---- per-device launch state ------------------------------------------------------------------

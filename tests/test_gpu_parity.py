@@ -363,6 +363,29 @@ def test_last_code_straddles_a_segment(codec, oracle, L, total_hint):
             codec.decode_host(extra.view(np.uint8), None, off, M, L)
 
 
+def test_mixed_density_batch_sorted_decode(codec, oracle):
+    """A batch whose records are heavy on average (escapes) is decoded with the waves sorted by bits per sample
+    (wave_hist_kernel / wave_scatter_kernel) and with heavy warps skipping the table: only the ORDER of decoding
+    changes.  Noise levels from 1 to 3000 interleaved wave by wave, several chunks, ragged last chunk; a corrupt
+    record is still reported."""
+    import deltarice_b200 as d
+    r = np.random.default_rng(21)
+    L, M, nw = 1200, 8, 2600                                          # (> 896 waves: the lane parser)
+    sig = np.array([1, 3, 10, 30, 100, 1000, 3000, 2])[np.arange(nw) % 8][:, None]
+    x = np.clip(np.rint(r.normal(0, 1, (nw, L)) * sig), -32768, 32767).astype(np.int16).ravel()[:-77]
+    off = d.chunk_offsets(300 * L, x.size)
+    want, wboff = _oracle_batch(oracle, x, off, M, L)
+    assert want.size * 32 > x.size * (3 + 5)                          # dense enough to take the sorted path
+    assert np.array_equal(codec.decode_host(want.view(np.uint8), wboff, off, M, L), x)
+    got, boff = codec.encode_host(x, off, M, L)
+    assert np.array_equal(got.view(np.uint32), want)
+    bad = want.copy()
+    bad[int(wboff[3]) // 4 + 1] += 1                                  # first record of chunk 3 claims one word too many
+    with pytest.raises(d.DeltaRiceError):
+        codec.decode_host(bad.view(np.uint8), wboff, off, M, L)
+    assert np.array_equal(codec.decode_host(want.view(np.uint8), wboff, off, M, L), x)
+
+
 def test_long_wave_capacity_and_filter(codec, oracle):
     """The several-CTAs-per-wave encoder: an output buffer that is too small is reported (nothing is written
     past it), and option tuples whose pre-filter is [1] (no delta) take the same kernels."""

@@ -1,3 +1,4 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "straddles or long" 2>&1 | tail -15
-python tools/small_chunk_breakdown.py 20 2>&1 | grep -E "decode|kernel times" | cut -c1-200
-python tools/small_chunk_breakdown.py 60 2>&1 | grep -E "device-resident decode|kernel times" | cut -c1-200
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --workload c4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2j_c4.json 2> gpurun_out/r2j_c4.err
+python bench.py --workload c3 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2j_c3.json 2> gpurun_out/r2j_c3.err
+python bench.py --steps 20 --warmup 3 > gpurun_out/r2j_c2.json 2> gpurun_out/r2j_c2.err

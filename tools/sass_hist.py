@@ -7,8 +7,8 @@ HOT = [  # (object glob, mangled-name regex, label)
     ("drice_encode_p0.o", r"encode_tile_kernelILi3ELi1ELb1ELi24ELi1E", "encode_tile_kernel<K=3, 1 CTA/SM, delta, 24 workers, table front-end>  (C3/C5: M = 8, L = 7000)"),
     ("drice_encode_p1.o", r"encode_tile_kernelILi4ELi2ELb1ELi12ELi0E", "encode_tile_kernel<K=4, arithmetic front-end>  (M = 16)"),
     ("drice_encode_p0.o", r"encode_long_pack_kernelILi3E", "encode_long_pack_kernel<K=3>  (few long waves)"),
-    ("drice_decode.o", r"[0-9]parse_kernelILb1ELb0E", "parse_kernel<W<=10 bits, delta>  (C2)"),
-    ("drice_decode.o", r"[0-9]parse_kernelILb0ELb0E", "parse_kernel<W>10 bits, delta>  (M = 8)"),
+    ("drice_decode.o", r"[0-9]parse_kernelILb1ELb0ELb0E", "parse_kernel<W<=10 bits, delta>  (C2)"),
+    ("drice_decode.o", r"[0-9]parse_kernelILb0ELb0ELb0E", "parse_kernel<W>10 bits, delta>  (M = 8)"),
     ("drice_decode.o", r"scan_headers_kernel", "scan_headers_kernel"),
     ("drice_decode.o", r"rank_headers_kernel", "rank_headers_kernel"),
     ("drice_decode.o", r"[0-9]locate_kernelE", "locate_kernel (header chase: bulk async copies, SASS UBLKCP + SYNCS mbarrier)"),
