@@ -684,6 +684,7 @@ extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_co
     // waves of similar density sharing a warp (drice_decode.cu: wave_hist_kernel / wave_scatter_kernel)
     static const int sort_env = [] { const char *v = getenv("DRICE_DEC_SORT"); return v ? atoi(v) : 1; }();
     const bool dense = sort_env == 2 || (sort_env == 1 && (woff[nchunks] - woff[0]) * 32ull > (off[nchunks] - off[0]) * (uint64_t)(k + 5));
+    const bool heavy_ok = dense || (woff[nchunks] - woff[0]) * 256ull > (off[nchunks] - off[0]) * (uint64_t)(8 * k + 28);   // (k + 3.5 bits: an escape in most groups of codes)
     const size_t scratch = zeroed + nw * (8 + 8 + 4) + 64 + 16 + (dense ? nw * 4 + 16 : 0);
     if (scratch > ctx->d_scratch.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
     DR_CUDA(ctx, ctx->d_scratch.reserve(scratch));
@@ -736,6 +737,7 @@ extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_co
     pp.identity = ctx->filter_mode != 0;
     pp.long_state = long_bytes ? (unsigned long long *)((char *)ctx->d_scratch.p + 16) : nullptr;
     pp.sort_counters = (uint32_t *)((char *)ctx->d_scratch.p + 16 + long_bytes);
+    pp.heavy_ok = heavy_ok ? 1 : 0;
     pp.sort_perm = dense ? (uint32_t *)(((uintptr_t)(wave_n + nw) + 15) & ~(uintptr_t)15) : nullptr;
     // widest store that every wave start allows
     int store_bytes = (int)(g.align_samples * 2);

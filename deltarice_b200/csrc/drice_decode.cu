@@ -1418,7 +1418,7 @@ int launch_parse_impl(const ParseParams &p, cudaStream_t st)
     const bool w10 = lut_bits_for(p.k) <= 10;
     // dense batches (the ones that are sorted): the instance whose heavy warps skip the table
     static const int heavy_env = [] { const char *v = getenv("DRICE_DEC_HEAVY"); return v ? atoi(v) : 1; }();
-    const bool hv = pp.sort_perm != nullptr && heavy_env != 0;
+    const bool hv = pp.heavy_ok != 0 && heavy_env != 0;
     auto go = [&](auto kern) { kern<<<grid, warps * 32, pp.smem_bytes, st>>>(pp); };
     if (hv) {
         if (p.identity) { if (w10) go(parse_kernel<true, true, true>); else go(parse_kernel<false, true, true>); }

@@ -101,6 +101,7 @@ struct ParseParams {
     // sort_perm: [nwaves] scratch; sort_counters: 16 zeroed words (histogram + cursors of 8 buckets)
     uint32_t       *sort_perm;
     uint32_t       *sort_counters;
+    int             heavy_ok;           // 1: the parser instance whose heavy warps skip the table (batches above k + 3.5 bits per sample)
 };
 
 // ---- per-device launch state ------------------------------------------------------------------
