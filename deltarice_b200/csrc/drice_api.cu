@@ -710,16 +710,20 @@ extern "C" int drice_decode_batch_dev_async(drice_ctx *ctx, const uint32_t *d_co
     lp.nchunks = (uint32_t)nchunks;
     lp.L = g.Lk;
     {
-        uint64_t max_chunk_words = 0;
-        for (size_t c = 0; c < nchunks; ++c) max_chunk_words = std::max<uint64_t>(max_chunk_words, woff[c + 1] - woff[c]);
+        uint64_t max_chunk_words = 0, max_chunk_waves = 0;
+        for (size_t c = 0; c < nchunks; ++c) {
+            max_chunk_words = std::max<uint64_t>(max_chunk_words, woff[c + 1] - woff[c]);
+            max_chunk_waves = std::max<uint64_t>(max_chunk_waves, g.wave_off[c + 1] - g.wave_off[c]);
+        }
         size_t scan_bytes = 0;
-        const bool scan = locate_scan_applies(g.Lk, k, max_chunk_words, nchunks, &scan_bytes);
+        const bool direct = g.Lk != 0 && locate_direct_applies(woff[nchunks] - woff[0], max_chunk_waves, nchunks);
+        const bool scan = !direct && locate_scan_applies(g.Lk, k, max_chunk_words, nchunks, &scan_bytes);
         if (scan) {
             if (scan_bytes > ctx->d_scan.cap) DR_CUDA(ctx, cudaDeviceSynchronize());
             DR_CUDA(ctx, ctx->d_scan.reserve(scan_bytes));
         }
         TimedScope ts(ctx, DRICE_KERNEL_LOCATE, st);
-        ctx->launches += (uint64_t)(scan ? launch_locate_scan(lp, k, max_chunk_words, ctx->d_scan.p, st) : launch_locate(lp, st));
+        ctx->launches += (uint64_t)(direct ? launch_locate_direct(lp, k, st) : scan ? launch_locate_scan(lp, k, max_chunk_words, max_chunk_waves, ctx->d_scan.p, st) : launch_locate(lp, st));
     }
 
     ParseParams pp{};

@@ -184,7 +184,10 @@ size_t encode_long_scratch_bytes(uint32_t nwaves, uint32_t max_wave_len);
 int launch_locate(const LocateParams &p, cudaStream_t st);
 // header scan instead of the chase (drice_decode.cu): applicability + scratch size, launcher
 bool locate_scan_applies(uint32_t L, int k, uint64_t max_chunk_words, size_t nchunks, size_t *scratch_bytes);
-int launch_locate_scan(const LocateParams &p, int k, uint64_t max_chunk_words, void *scratch, cudaStream_t st);
+int launch_locate_scan(const LocateParams &p, int k, uint64_t max_chunk_words, uint64_t max_chunk_waves, void *scratch, cudaStream_t st);
+// very large batches: one warp per chunk walks the chain through global memory (cheaper than reading the whole stream)
+bool locate_direct_applies(uint64_t comp_words, uint64_t max_chunk_waves, size_t nchunks);
+int launch_locate_direct(const LocateParams &p, int k, cudaStream_t st);
 int launch_parse(const ParseParams &p, int store_bytes, cudaStream_t st);
 size_t parse_long_state_bytes(uint32_t nwaves, uint32_t max_n);
 // out[i] = sum_j in[i-j] * f[j] per wave (mod 2^16); in != out

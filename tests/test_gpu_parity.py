@@ -182,6 +182,22 @@ def test_header_chase_on_the_small_cases():
     assert " passed" in r.stdout
 
 
+def test_direct_chase_on_the_small_cases():
+    """Very large batches locate their records with one warp per chunk walking the chain through global memory
+    (chase_direct_kernel) instead of the header scan.  DRICE_LOCATE_DIRECT=1 sends every scannable batch there."""
+    import subprocess
+    import sys
+    if os.environ.get("DRICE_LOCATE_DIRECT"):
+        pytest.skip("already running under the override")
+    env = dict(os.environ, DRICE_LOCATE_DIRECT="1")
+    sel = ("single_chunk_host_path or golden or ragged_batch or unaligned_pointers or many_chunks or readme_config "
+           "or errors or full_size_c2 or mixed_density")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", sel],
+                       env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout
+
+
 def test_lane_parser_on_the_small_cases():
     """Batches of up to 896 waves (<= 8192 samples each) are decoded by parse_wide_kernel (one CTA
     per wave, parallel inside the wave), larger ones by parse_kernel (one lane per wave).
