@@ -206,8 +206,12 @@ __global__ void __launch_bounds__(kLocThreads) locate_kernel(const LocateParams 
                 wi += 4;
                 left -= 4u;
                 pos = p4;
-            } else if (pos >= avail || (avail < end_b && left >= 4u)) {
-                // out of loaded data (or too close to its end for four hops): take the next tile in
+            } else if (pos >= avail || (avail < end_b && left >= 4u && tiles_in - tiles_out < (uint32_t)kLocStages)) {
+                // out of loaded data (or too close to its end for four hops): take the next tile in.
+                // (Only while a stage is free: four records that do not fit the ring together - waves of more
+                // than ~10000 samples of pure noise, which only come here under DRICE_LOCATE_SCAN=0 - would have
+                // the chaser wait for a tile the producer cannot issue before the chaser releases one; such
+                // records are walked one hop at a time below.)
                 mbar_wait(full_s + 8u * (tiles_in % kLocStages), (tiles_in / kLocStages) & 1u);
                 ++tiles_in;
                 const uint32_t te = tiles_in * kTileBytes;
