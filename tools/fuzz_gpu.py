@@ -1,6 +1,7 @@
 """Randomised parity runs against the oracle (bit-exact stream, exact round trip, oracle stream decodes):
 python tools/fuzz_gpu.py [iterations] [seed].  Shapes cover tiny and mid-size batches, ragged chunks, every
-Rice parameter class, long waves, whole-chunk waves, mixed noise levels (escape-heavy waves next to quiet ones)."""
+Rice parameter class, long waves, whole-chunk waves, mixed noise levels (escape-heavy waves next to quiet ones).
+Run it under `timeout` on the GPU box: a kernel that hangs would otherwise hold the box until its limit."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
