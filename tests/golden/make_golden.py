@@ -35,6 +35,16 @@ def cases():
     out.append(("escape_heavy", r.integers(-32768, 32768, 7000).astype(np.int16), (2, 3500)))
     out.append(("exact_word", np.zeros(16, np.int16), (8, 8)))
     out.append(("long_wave_20000", r.normal(0, 25, 40000).astype(np.int16), (8, 20000)))
+    # round 2: the shapes the several-CTAs-per-wave kernels and the density sort take
+    out.append(("default_opts_whole_chunk", r.normal(0, 30, 50001).astype(np.int16), ()))          # RiceParameter 8, one wave
+    out.append(("whole_chunk_m4", np.cumsum(r.normal(0, 3, 120001)).astype(np.int16), (4,)))
+    out.append(("long_wave_81920", r.normal(0, 6, 81920 * 2).astype(np.int16), (8, 81920)))
+    out.append(("long_wave_ragged", r.normal(0, 200, 30000 * 2 + 12345).astype(np.int16), (16, 30000)))
+    sig = np.array([1, 3, 10, 30, 100, 1000, 3000, 2])[np.arange(40) % 8][:, None]
+    out.append(("mixed_density", np.clip(np.rint(r.normal(0, 1, (40, 1200)) * sig), -32768, 32767).astype(np.int16).ravel(), (8, 1200)))
+    # a short last wave whose LAST code starts in the record's 256th word and ends in its 257th
+    tail = np.clip(np.rint(np.cumsum(np.random.default_rng(11).normal(0, 6, 40000))), -32768, 32767).astype(np.int16)[:1728]
+    out.append(("last_code_straddles_256_words", np.concatenate([r.normal(0, 6, 6000 * 3).astype(np.int16), tail]), (8, 6000)))
     return out
 
 
