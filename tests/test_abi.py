@@ -25,6 +25,20 @@ def test_library_exports_every_declared_symbol():
     assert L.drice_abi_version() == 2
 
 
+def test_headers_compile_as_c_and_cxx():
+    """include/*.h is the drop-in boundary: plain C (what the reference's C callers compile) and C++."""
+    import glob, shutil, subprocess
+    if not shutil.which("gcc") or not shutil.which("g++"):
+        pytest.skip("no host compiler")
+    inc = os.path.join(ROOT, "include")
+    shim = os.path.join(ROOT, "oracle", "hdf5_shim")       # (deltaRice.h includes <hdf5.h> under DRICE_USE_SYSTEM_HDF5 only)
+    for h in sorted(glob.glob(os.path.join(inc, "*.h"))):
+        for cc, std, lang in (("gcc", "-std=c99", "c"), ("g++", "-std=c++17", "c++")):
+            r = subprocess.run([cc, std, "-Wall", "-Werror", "-fsyntax-only", "-x", lang, "-I", inc, "-I", shim, h],
+                               capture_output=True, text=True)
+            assert r.returncode == 0, f"{cc} {h}: {r.stderr[:500]}"
+
+
 def test_h5_class_struct_matches_reference():
     # reference src/deltaRice.c:19-28: {vers 1, id 32025, enc 1, dec 1, "deltarice", NULL, NULL, filter}
     L = _lib.load()
