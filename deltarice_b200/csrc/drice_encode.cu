@@ -827,15 +827,14 @@ __device__ __noinline__ void encode_wave_lut_in_place(const int16_t *wave, uint3
 //     aggregate at once (nobody ever waits for a size that is already known);
 //   * the control warp resolves tile after tile by decoupled look-back and hands the offsets to
 //     the workers through shared memory, one iteration behind them.
-// Shared control state lives in a ring of 3 slots (iteration % 3): a slot is reused only after
-// the workers have copied out the tile two iterations back, which needs the control warp to be
-// done with it.
+// Shared control state lives in a ring of kRing slots (iteration % kRing): a slot is reused only after
+// the workers have copied out the tile of that slot, which needs the control warp to be done with it.
 constexpr int kRing = 4;                                  // per-tile state: previous / current / next + one a fast worker has moved on to
 constexpr int kTileRing = 8;                              // tile indices, published three iterations ahead
 
-// NW worker warps (+ 1 control warp) per CTA: 12 for short waves (two CTAs per SM: measured best,
-// 0.69 vs 0.74 ms for 3 x 8 on C2; 13 and 14 lose to register pressure), 8 when the staging of
-// longer waves needs the room
+// NW worker warps (+ 1 control warp) per CTA: 24 in one CTA per SM (best since the workers run without a
+// barrier between them), 12 in two CTAs or 8 when the staging of longer records needs the room, 8 in two
+// CTAs for small batches (launch_k)
 // LUT: 0 = arithmetic front-end (encode_round), 1 = table front-end (1 <= K <= 6), 16 samples per lane and round
 // (32 per lane were measured too: twice as slow - registers spill and the unrolled round outgrows the
 // instruction cache)
@@ -944,9 +943,10 @@ encode_tile_kernel(const EncodeParams p, const uint32_t stage_words, const uint3
     }
 
     // ---- workers ---------------------------------------------------------------------------
-    // Tickets are taken ONE tile ahead (s_tile[(it + 1) % kRing] is known during iteration it), so a worker
-    // sets up its next wave - geometry and, for the table front-end, the first round's words - before it
-    // copies out the previous one: the loads fly during the copy-out and the tile barrier.
+    // Tile indices are published ahead of their iteration (s_tile / s_tseq: the first three of a CTA are fixed,
+    // later ones are tickets warp 0 takes during iteration it for iteration it + 3), so a worker sets up its
+    // next wave - geometry and, for the table front-end, the first round's words - before it copies out the
+    // previous one: the loads fly during the copy-out.
     uint32_t *const stage0 = smem + (size_t)(2 * warp) * stage_words;   // two staging buffers per warp
     const int16_t *const raw_hi = p.raw + p.raw_samples;
     uint32_t largest = 0;                                // largest record of this warp (sizes the next batch's staging)
