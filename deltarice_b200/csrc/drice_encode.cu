@@ -1551,10 +1551,11 @@ encode_long_pack_kernel(const LongParams lp)
 // worker warp (+ the pair table); a wave that outgrows its staging is packed a second time straight into
 // its record, so the staging should hold the batch's largest record: it is sized from the largest record
 // of the context's previous batch of the same shape (`words_hint`, + 1/16), else for 10 bits per sample.
-// More resident worker warps beat larger staging (measured, L = 7000: 2 x 12 warps 0.44 ms, 1 x 24 0.45,
-// 1 x 20 0.48, 1 x 12 0.65, 1 x 8 0.90), so the geometries are tried in that order and the first one
-// whose staging holds `want` words wins; without a hint the first geometry is taken with all the
-// staging it has room for.
+// More resident worker warps beat larger staging (measured with a barrier per tile, L = 7000: 2 x 12 warps
+// 0.44 ms, 1 x 24 0.45, 1 x 20 0.48, 1 x 12 0.65, 1 x 8 0.90; without the barrier 1 x 24 is the best: C2 0.530
+// against 0.559 for 2 x 12), so the geometries 1 x 24, 2 x 12, 2 x 8, 1 x 8 are tried in that order and the
+// first one whose staging holds `want` words wins; without a hint the first geometry is taken with all the
+// staging it has room for.  Small batches take 8-wave tiles (more SMs, less contention per wave).
 struct TileGeom { int workers, ctas; };
 
 template <int K>
