@@ -13,14 +13,20 @@
 //   locate_kernel  short waves / very long waves: one CTA per chunk streams the chunk through a
 //                  128 KB circular buffer in shared memory (bulk async copies on mbarriers) while ONE
 //                  thread chases the chain at shared-memory latency
+//   chase_direct_kernel   very large batches: one warp per chunk walks the chain through global memory
+//                  (every chunk at once: cheaper than reading tens of GB of stream to find the headers)
 // Decoding the records:
 //   parse_kernel   one LANE per wave, 32 waves per warp: Rice parsing is a serial chain per wave, so
 //                  the parallelism is across waves.  One register of state per lane
 //                  (sample << 16 | bit position), one table lookup and one add per code, several
-//                  codes per 64-bit window, 16 samples per 32-byte store
+//                  codes per 64-bit window, 16 samples per 32-byte store.  Batches with heavy records
+//                  (escapes) take the HEAVY instance: waves sorted by bits per sample first
+//                  (wave_hist_kernel / wave_scatter_kernel), and warps of heavy waves skip the table
 //   parse_wide_kernel   batches too small to fill the machine with lanes: one CTA per wave,
 //                  parallel INSIDE the wave (transition functions of four-word runs composed along
 //                  the record, then the runs decode independently)
+//   parse_long_kernel   few waves of many words (or a handful of short ones): several CTAs per wave,
+//                  segments of 256 ... 6400 words chained along the record
 #include "drice_kernels.cuh"
 
 #include <cstdio>
